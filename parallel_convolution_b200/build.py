@@ -1,0 +1,135 @@
+"""In-tree native build: g++ for the host library, nvcc (sm_100a only) for the CUDA library.
+
+The shared objects land in ``parallel_convolution_b200/_lib/`` (git-ignored, but they travel to
+the GPU box with the gpurun snapshot). ``python -m parallel_convolution_b200.build`` builds
+everything; ``ensure_host()`` / ``ensure_cuda()`` rebuild lazily when a source is newer.
+
+There is exactly one GPU target: ``-gencode arch=compute_100a,code=sm_100a`` (B200). No
+multi-arch fatbin, no fallback path.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "_lib"
+
+HOST_LIB = LIB / "libpconv_host.so"
+CUDA_LIB = LIB / "libpconv_cuda.so"
+NATIVE_BIN = LIB / "pconv_native"
+
+NVCC = os.environ.get("PCONV_NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+def _pick_cxx() -> str:
+    # /opt/gcc/bin/g++ (first on PATH in this image) is a wrapper without libgomp.spec; the
+    # distro compiler links OpenMP fine. CXX in the environment only wins when it is a path we
+    # can actually run.
+    for cand in ("/usr/bin/g++", os.environ.get("PCONV_CXX"), shutil.which("g++")):
+        if cand and Path(cand).exists():
+            return cand
+    return "g++"
+
+
+CXX = _pick_cxx()
+
+HOST_SOURCES = ["host/filters.cpp", "host/decomp.cpp", "host/cpu_engine.cpp", "host/rawio.cpp"]
+HOST_ORACLE = "host/oracle.cpp"  # compiled separately at -O1 with contraction off
+CUDA_SOURCES = ["cuda/runtime.cu", "cuda/stream_kernel.cu", "cuda/resident_kernel.cu",
+                "cuda/pack_kernels.cu"]
+
+CXXFLAGS = ["-std=c++17", "-fPIC", "-O3", "-ffp-contract=off", "-fopenmp", "-Wall",
+            "-Wno-unknown-pragmas"]
+NVCCFLAGS = ["-ccbin", CXX, "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+             "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--fmad=false"]
+
+
+def _run(cmd: list[str], log: Path | None = None) -> None:
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if log is not None:
+        log.write_text(" ".join(cmd) + "\n" + proc.stdout)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout)
+        raise RuntimeError(f"build step failed ({proc.returncode}): {' '.join(cmd)}")
+
+
+def _stale(target: Path, sources: list[Path]) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(s.stat().st_mtime > t for s in sources if s.exists())
+
+
+def _all_headers() -> list[Path]:
+    return list(CSRC.rglob("*.h")) + list(CSRC.rglob("*.cuh"))
+
+
+def build_host(force: bool = False) -> Path:
+    LIB.mkdir(exist_ok=True)
+    srcs = [CSRC / s for s in HOST_SOURCES] + [CSRC / HOST_ORACLE]
+    if not force and not _stale(HOST_LIB, srcs + _all_headers()):
+        return HOST_LIB
+    objs = []
+    for s in HOST_SOURCES:
+        o = LIB / (Path(s).stem + ".o")
+        _run([CXX, *CXXFLAGS, "-c", str(CSRC / s), "-o", str(o)])
+        objs.append(str(o))
+    o = LIB / "oracle.o"
+    _run([CXX, "-std=c++17", "-fPIC", "-O1", "-ffp-contract=off", "-fno-tree-vectorize",
+          "-c", str(CSRC / HOST_ORACLE), "-o", str(o)])
+    objs.append(str(o))
+    _run([CXX, "-shared", "-fopenmp", "-o", str(HOST_LIB), *objs])
+    return HOST_LIB
+
+
+def build_cuda(force: bool = False) -> Path:
+    LIB.mkdir(exist_ok=True)
+    srcs = [CSRC / s for s in CUDA_SOURCES if (CSRC / s).exists()]
+    if not force and not _stale(CUDA_LIB, srcs + _all_headers()):
+        return CUDA_LIB
+    if not Path(NVCC).exists():
+        raise RuntimeError(f"nvcc not found at {NVCC}; the CUDA library cannot be built")
+    objs = []
+    for s in srcs:
+        o = LIB / (s.stem + ".cu.o")
+        _run([NVCC, *NVCCFLAGS, "-c", str(s), "-o", str(o)], log=LIB / (s.stem + ".ptxas.log"))
+        objs.append(str(o))
+    _run([NVCC, "-ccbin", CXX, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(CUDA_LIB),
+          *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    return CUDA_LIB
+
+
+def build_native(force: bool = False) -> Path | None:
+    """Stand-alone C++ CLI (drop-in for the reference's ./cuda_conv on one GPU, CPU fallback)."""
+    main = CSRC / "native_main.cpp"
+    if not main.exists():
+        return None
+    build_host(force)
+    build_cuda(force)
+    if not force and not _stale(NATIVE_BIN, [main, HOST_LIB, CUDA_LIB]):
+        return NATIVE_BIN
+    _run([CXX, "-std=c++17", "-O2", str(main), "-o", str(NATIVE_BIN), f"-L{LIB}",
+          "-lpconv_host", "-lpconv_cuda", "-Wl,-rpath,$ORIGIN", "-fopenmp"])
+    return NATIVE_BIN
+
+
+def ensure_host() -> Path:
+    return build_host(False)
+
+
+def ensure_cuda() -> Path:
+    return build_cuda(False)
+
+
+def build_all(force: bool = False) -> None:
+    build_host(force)
+    build_cuda(force)
+    build_native(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)
+    print("built:", *[p for p in (HOST_LIB, CUDA_LIB, NATIVE_BIN) if p.exists()], sep="\n  ")

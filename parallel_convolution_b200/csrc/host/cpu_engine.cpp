@@ -1,0 +1,131 @@
+// CPU engine: the B200 framework's stand-in for the reference's mpi_conv / mpi_omp_conv compute
+// (convolute/convolute_grey/convolute_rgb, mpi/mpi_conv.c:299-333 and the OpenMP worksharing of
+// mpi_omp/mpi_omp_conv.c:297-310). Differences by design, not translation:
+//   * grey and RGB are the same loop: an interleaved image is a byte stream whose horizontal
+//     neighbour is C bytes away, so one kernel serves any channel count;
+//   * row kernels are written to auto-vectorise (AVX2/AVX-512 clones) instead of a call per pixel
+//     through float** (SURVEY.md §3.1);
+//   * the integer path is used exactly when it is provably identical to the fp32 oracle
+//     (filters.cpp); the fp32 path keeps the oracle's tap order and is compiled with
+//     -ffp-contract=off, so both are byte-exact;
+//   * OpenMP parallelises rows with one parallel region per pass (the reference opens one per
+//     convolute() call, including 1x1 corner calls, and its pragma does not compile: defect D7).
+#include <omp.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "pconv_host.h"
+
+#define PCONV_CLONES __attribute__((target_clones("default", "avx2", "arch=x86-64-v4")))
+
+namespace {
+
+// ---- one output row, n bytes, neighbour distance C bytes -------------------------------------
+
+PCONV_CLONES void row_int(const uint8_t* __restrict up, const uint8_t* __restrict mid,
+                          const uint8_t* __restrict dn, uint8_t* __restrict out, int64_t n,
+                          int C, const int32_t* w, int shift) {
+    const short w0 = (short)w[0], w1 = (short)w[1], w2 = (short)w[2];
+    const short w3 = (short)w[3], w4 = (short)w[4], w5 = (short)w[5];
+    const short w6 = (short)w[6], w7 = (short)w[7], w8 = (short)w[8];
+    for (int64_t x = 0; x < n; ++x) {
+        // |S| <= sum|w| * 255 <= 32640: fits 16-bit lanes (filters.cpp guarantees sum|w| <= 128)
+        short s = (short)(w0 * up[x - C] + w1 * up[x] + w2 * up[x + C] + w3 * mid[x - C] +
+                          w4 * mid[x] + w5 * mid[x + C] + w6 * dn[x - C] + w7 * dn[x] +
+                          w8 * dn[x + C]);
+        short v = (short)(s >> shift);  // arithmetic shift: floor; negatives clamp to 0 below
+        v = v < 0 ? (short)0 : v;
+        v = v > 255 ? (short)255 : v;
+        out[x] = (uint8_t)v;
+    }
+}
+
+PCONV_CLONES void row_sep121(const uint8_t* __restrict up, const uint8_t* __restrict mid,
+                             const uint8_t* __restrict dn, uint8_t* __restrict out, int64_t n,
+                             int C) {
+    for (int64_t x = 0; x < n; ++x) {
+        // vertical [1 2 1] first (<= 1020), then horizontal (<= 4080), then >> 4: exact Gaussian/16
+        const unsigned short vl = (unsigned short)(up[x - C] + 2 * mid[x - C] + dn[x - C]);
+        const unsigned short vc = (unsigned short)(up[x] + 2 * mid[x] + dn[x]);
+        const unsigned short vr = (unsigned short)(up[x + C] + 2 * mid[x + C] + dn[x + C]);
+        out[x] = (uint8_t)((unsigned short)(vl + 2 * vc + vr) >> 4);
+    }
+}
+
+PCONV_CLONES void row_f32(const uint8_t* __restrict up, const uint8_t* __restrict mid,
+                          const uint8_t* __restrict dn, uint8_t* __restrict out, int64_t n,
+                          int C, const float* h) {
+    const float h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3], h4 = h[4], h5 = h[5], h6 = h[6],
+                h7 = h[7], h8 = h[8];
+    for (int64_t x = 0; x < n; ++x) {
+        float v = 0.0f;  // oracle order; -ffp-contract=off keeps mul and add separately rounded
+        v = v + (float)up[x - C] * h0;
+        v = v + (float)up[x] * h1;
+        v = v + (float)up[x + C] * h2;
+        v = v + (float)mid[x - C] * h3;
+        v = v + (float)mid[x] * h4;
+        v = v + (float)mid[x + C] * h5;
+        v = v + (float)dn[x - C] * h6;
+        v = v + (float)dn[x] * h7;
+        v = v + (float)dn[x + C] * h8;
+        v = v > 0.0f ? v : 0.0f;
+        v = v < 255.0f ? v : 255.0f;
+        out[x] = (uint8_t)(int)v;
+    }
+}
+
+inline void one_row(const uint8_t* src0, uint8_t* dst0, int64_t pitch, int C,
+                    const pconv_filter_t* f, int64_t y, int64_t c0, int64_t c1) {
+    const int64_t b0 = c0 * C, n = (c1 - c0) * C;
+    const uint8_t* mid = src0 + y * pitch + b0;
+    const uint8_t* up = mid - pitch;
+    const uint8_t* dn = mid + pitch;
+    uint8_t* out = dst0 + y * pitch + b0;
+    switch (f->kind) {
+        case PCONV_KIND_SEP121: row_sep121(up, mid, dn, out, n, C); break;
+        case PCONV_KIND_INT: row_int(up, mid, dn, out, n, C, f->w, f->shift); break;
+        default: row_f32(up, mid, dn, out, n, C, f->h); break;
+    }
+}
+
+}  // namespace
+
+extern "C" int pconv_omp_max_threads(void) { return omp_get_max_threads(); }
+
+extern "C" int pconv_cpu_convolve(const uint8_t* src0, uint8_t* dst0, int64_t pitch, int C,
+                                  const pconv_filter_t* f, int64_t r0, int64_t r1, int64_t c0,
+                                  int64_t c1, int threads) {
+    if (!src0 || !dst0 || !f || C <= 0) return -1;
+    if (r1 <= r0 || c1 <= c0) return 0;
+    const int nt = threads > 0 ? threads : omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(nt) if (nt > 1 && (r1 - r0) > 1)
+    for (int64_t y = r0; y < r1; ++y) one_row(src0, dst0, pitch, C, f, y, c0, c1);
+    return 0;
+}
+
+extern "C" int pconv_cpu_run_image(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
+                                   const pconv_filter_t* f, int loops, int threads) {
+    if (!src || !dst || !f || H <= 0 || W <= 0 || C <= 0 || loops < 0) return -1;
+    const int64_t rb = W * (int64_t)C;
+    if (loops == 0) {
+        std::memcpy(dst, src, (size_t)(H * rb));
+        return 0;
+    }
+    // Two zero-initialised padded buffers: the 1-pixel frame stays 0 forever = zero padding
+    // (same device the reference uses: calloc'd (rows+2)x(cols+2) tiles, mpi/mpi_conv.c:113-124).
+    const int64_t pitch = ((rb + 2 * C + 63) / 64) * 64;
+    std::vector<uint8_t> a((size_t)((H + 2) * pitch), 0), b((size_t)((H + 2) * pitch), 0);
+    uint8_t* pa = a.data() + pitch + C;
+    uint8_t* pb = b.data() + pitch + C;
+    for (int64_t y = 0; y < H; ++y) std::memcpy(pa + y * pitch, src + y * rb, (size_t)rb);
+    for (int t = 0; t < loops; ++t) {
+        pconv_cpu_convolve(pa, pb, pitch, C, f, 0, H, 0, W, threads);
+        std::swap(pa, pb);
+    }
+    for (int64_t y = 0; y < H; ++y) std::memcpy(dst + y * rb, pa + y * pitch, (size_t)rb);
+    return 0;
+}

@@ -1,0 +1,71 @@
+// C ABI of libpconv_host.so — the CPU side of the framework (no CUDA dependency).
+// Loaded from Python through ctypes (parallel_convolution_b200/ops/host.py) and linked into the
+// native CLI (csrc/native_main.cpp).
+#ifndef PCONV_HOST_H
+#define PCONV_HOST_H
+
+#include <stdint.h>
+#include "../common/pconv_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// ---- filters (models/filters.py is the Python face of these) --------------------------------
+// Build a filter from integer numerators and a divisor the way the reference does
+// (h = (float)(w / (double)div), mpi/mpi_conv.c:98-107) and classify the exact fast path.
+int pconv_filter_from_int(const int32_t w[9], double div, pconv_filter_t* out);
+// Build from arbitrary fp32 taps (classified INT when every tap is n/2^s with small n).
+int pconv_filter_from_float(const float h[9], pconv_filter_t* out);
+
+// ---- decomposition (reference: divide_rows, mpi/mpi_conv.c:363-377) --------------------------
+// Reference-compatible chooser: returns rows-of-tiles, 0 when no exact division exists.
+int pconv_divide_rows(int64_t rows, int64_t cols, int workers);
+// Extended chooser: exact division when possible (identical to the reference), else the
+// perimeter-minimising grid with remainder tiles. Returns 0 on success.
+int pconv_choose_grid(int64_t rows, int64_t cols, int workers, int* row_div, int* col_div,
+                      int* exact);
+// Balanced 1-D split with remainder: part idx of `parts` over [0, extent).
+void pconv_split(int64_t extent, int parts, int idx, int64_t* start, int64_t* size);
+
+// ---- oracle: whole image, zero padded, scalar, deliberately naive ----------------------------
+// src/dst: H x (W*C) bytes, dense. Applies the filter `loops` times; result is in dst.
+// scratch must hold H*W*C bytes (ping-pong partner). Returns 0.
+int pconv_oracle_run(const uint8_t* src, uint8_t* dst, uint8_t* scratch, int64_t H, int64_t W,
+                     int C, const pconv_filter_t* f, int loops);
+
+// ---- CPU engine: one iteration over a rectangle of a halo-padded tile ------------------------
+// `src0`/`dst0` point at pixel (0,0) of the tile interior; every computed pixel must have a
+// valid 1-pixel halo around it in src (the caller owns the padding). Rows [r0,r1), pixel
+// columns [c0,c1). `threads` <= 0 means "use OpenMP default".
+int pconv_cpu_convolve(const uint8_t* src0, uint8_t* dst0, int64_t pitch, int C,
+                       const pconv_filter_t* f, int64_t r0, int64_t r1, int64_t c0, int64_t c1,
+                       int threads);
+// Whole dense image, `loops` iterations, zero padded, multi-threaded; dst receives the result.
+int pconv_cpu_run_image(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
+                        const pconv_filter_t* f, int loops, int threads);
+int pconv_omp_max_threads(void);
+
+// ---- raw image I/O (64-bit offsets; reference: MPI_File_* mpi/mpi_conv.c:133-147,253-271) ----
+int64_t pconv_file_size(const char* path);
+// Read a rectangle: rows [row0,row0+nrows), bytes [byte0,byte0+nbytes) of every row of a file
+// whose rows are `row_bytes` long, into dst with `dst_pitch`. Returns 0 or -errno (-EIO on a
+// short file — the reference spins forever there, cuda/funcs.c:39-45).
+int pconv_read_rect(const char* path, int64_t row_bytes, int64_t row0, int64_t nrows,
+                    int64_t byte0, int64_t nbytes, uint8_t* dst, int64_t dst_pitch);
+// Create/truncate the output to its full size (rank 0 calls this once before the tiles land).
+int pconv_create_file(const char* path, int64_t total_bytes);
+int pconv_write_rect(const char* path, int64_t row_bytes, int64_t row0, int64_t nrows,
+                     int64_t byte0, int64_t nbytes, const uint8_t* src, int64_t src_pitch);
+
+// ---- synthetic images: value of byte i of the whole image = hash(seed, i) ---------------------
+// Independent of the decomposition, so any rank can generate exactly its own tile.
+void pconv_synth_rect(uint64_t seed, int64_t row_bytes, int64_t row0, int64_t nrows,
+                      int64_t byte0, int64_t nbytes, uint8_t* dst, int64_t dst_pitch);
+
+const char* pconv_host_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,182 @@
+"""ctypes binding of ``libpconv_host.so`` (csrc/host/pconv_host.h).
+
+Everything that runs on the CPU is native C++: the oracle, the vectorised/OpenMP CPU engine
+(the framework's analogue of the reference's ``mpi_conv`` / ``mpi_omp_conv`` compute), raw I/O,
+the decomposition chooser and the synthetic-image generator. Python only marshals pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from functools import lru_cache
+
+import numpy as np
+
+from .. import build as _build
+
+KIND_F32, KIND_INT, KIND_SEP121 = 0, 1, 2
+KIND_NAMES = {KIND_F32: "f32-exact", KIND_INT: "int-swar", KIND_SEP121: "sep121-swar"}
+
+
+class FilterSpec(C.Structure):
+    """Mirror of ``pconv_filter_t`` (csrc/common/pconv_types.h)."""
+
+    _fields_ = [("h", C.c_float * 9), ("w", C.c_int32 * 9), ("shift", C.c_int32),
+                ("kind", C.c_int32)]
+
+    def taps(self) -> np.ndarray:
+        return np.array(list(self.h), dtype=np.float32).reshape(3, 3)
+
+    def weights(self) -> np.ndarray:
+        return np.array(list(self.w), dtype=np.int32).reshape(3, 3)
+
+
+@lru_cache(maxsize=1)
+def lib() -> C.CDLL:
+    path = _build.ensure_host()
+    L = C.CDLL(os.fspath(path))
+    i64, u8p, fsp = C.c_int64, C.c_void_p, C.POINTER(FilterSpec)
+    L.pconv_filter_from_int.argtypes = [C.POINTER(C.c_int32), C.c_double, fsp]
+    L.pconv_filter_from_float.argtypes = [C.POINTER(C.c_float), fsp]
+    L.pconv_divide_rows.argtypes = [i64, i64, C.c_int]
+    L.pconv_choose_grid.argtypes = [i64, i64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int)]
+    L.pconv_split.argtypes = [i64, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)]
+    L.pconv_split.restype = None
+    L.pconv_oracle_run.argtypes = [u8p, u8p, u8p, i64, i64, C.c_int, fsp, C.c_int]
+    L.pconv_cpu_convolve.argtypes = [u8p, u8p, i64, C.c_int, fsp, i64, i64, i64, i64, C.c_int]
+    L.pconv_cpu_run_image.argtypes = [u8p, u8p, i64, i64, C.c_int, fsp, C.c_int, C.c_int]
+    L.pconv_file_size.argtypes = [C.c_char_p]
+    L.pconv_file_size.restype = i64
+    L.pconv_read_rect.argtypes = [C.c_char_p, i64, i64, i64, i64, i64, u8p, i64]
+    L.pconv_create_file.argtypes = [C.c_char_p, i64]
+    L.pconv_write_rect.argtypes = [C.c_char_p, i64, i64, i64, i64, i64, u8p, i64]
+    L.pconv_synth_rect.argtypes = [C.c_uint64, i64, i64, i64, i64, i64, u8p, i64]
+    L.pconv_synth_rect.restype = None
+    L.pconv_host_version.restype = C.c_char_p
+    return L
+
+
+def _ptr(a: np.ndarray) -> int:
+    assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"], "uint8 C-contiguous array required"
+    return a.ctypes.data
+
+
+def filter_from_int(w, div: float) -> FilterSpec:
+    arr = (C.c_int32 * 9)(*[int(v) for v in np.asarray(w).reshape(-1)])
+    f = FilterSpec()
+    if lib().pconv_filter_from_int(arr, float(div), C.byref(f)) != 0:
+        raise ValueError("bad integer filter (zero divisor?)")
+    return f
+
+
+def filter_from_float(h) -> FilterSpec:
+    arr = (C.c_float * 9)(*[float(v) for v in np.asarray(h, dtype=np.float32).reshape(-1)])
+    f = FilterSpec()
+    if lib().pconv_filter_from_float(arr, C.byref(f)) != 0:
+        raise ValueError("bad float filter")
+    return f
+
+
+def divide_rows(rows: int, cols: int, workers: int) -> int:
+    return int(lib().pconv_divide_rows(rows, cols, workers))
+
+
+def choose_grid(rows: int, cols: int, workers: int) -> tuple[int, int, bool]:
+    r, c, e = C.c_int(), C.c_int(), C.c_int()
+    rc = lib().pconv_choose_grid(rows, cols, workers, C.byref(r), C.byref(c), C.byref(e))
+    if rc != 0:
+        raise ValueError(f"cannot decompose {rows}x{cols} over {workers} workers")
+    return r.value, c.value, bool(e.value)
+
+
+def split(extent: int, parts: int, idx: int) -> tuple[int, int]:
+    s, n = C.c_int64(), C.c_int64()
+    lib().pconv_split(extent, parts, idx, C.byref(s), C.byref(n))
+    return s.value, n.value
+
+
+def oracle(image: np.ndarray, f: FilterSpec, loops: int) -> np.ndarray:
+    """Golden reference. ``image``: (H, W) or (H, W, C) uint8."""
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    H, W = img.shape[:2]
+    Cn = 1 if img.ndim == 2 else img.shape[2]
+    out, scratch = np.empty_like(img), np.empty_like(img)
+    rc = lib().pconv_oracle_run(_ptr(img), _ptr(out), _ptr(scratch), H, W, Cn, C.byref(f), loops)
+    if rc != 0:
+        raise RuntimeError(f"oracle failed ({rc})")
+    return out
+
+
+def cpu_run_image(image: np.ndarray, f: FilterSpec, loops: int, threads: int = 0) -> np.ndarray:
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    H, W = img.shape[:2]
+    Cn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty_like(img)
+    rc = lib().pconv_cpu_run_image(_ptr(img), _ptr(out), H, W, Cn, C.byref(f), loops, threads)
+    if rc != 0:
+        raise RuntimeError(f"cpu engine failed ({rc})")
+    return out
+
+
+def cpu_convolve(src: np.ndarray, dst: np.ndarray, halo: int, Cn: int, f: FilterSpec,
+                 r0: int, r1: int, c0: int, c1: int, threads: int = 0) -> None:
+    """One pass over rows [r0,r1) x pixel columns [c0,c1) of a halo-padded tile.
+
+    ``src``/``dst``: 2-D uint8 arrays (rows+2*halo, pitch) whose interior pixel (0,0) sits at
+    [halo, halo*Cn]. Coordinates may be negative / exceed the interior as long as the 1-pixel
+    stencil footprint stays inside the padded array (used by the k-deep temporal blocking of
+    the host backend).
+    """
+    assert src.shape == dst.shape and src.ndim == 2
+    pitch = src.strides[0]
+    off = halo * pitch + halo * Cn
+    rc = lib().pconv_cpu_convolve(src.ctypes.data + off, dst.ctypes.data + off, pitch, Cn,
+                                  C.byref(f), r0, r1, c0, c1, threads)
+    if rc != 0:
+        raise RuntimeError(f"cpu_convolve failed ({rc})")
+
+
+def file_size(path: str) -> int:
+    n = int(lib().pconv_file_size(os.fsencode(path)))
+    if n < 0:
+        raise OSError(-n, os.strerror(-n), path)
+    return n
+
+
+def read_rect(path: str, row_bytes: int, row0: int, nrows: int, byte0: int, nbytes: int,
+              out: np.ndarray | None = None) -> np.ndarray:
+    if out is None:
+        out = np.empty((nrows, nbytes), dtype=np.uint8)
+    assert out.dtype == np.uint8 and out.strides[1] == 1
+    rc = lib().pconv_read_rect(os.fsencode(path), row_bytes, row0, nrows, byte0, nbytes,
+                               out.ctypes.data, out.strides[0])
+    if rc != 0:
+        raise OSError(-rc, os.strerror(-rc), path)
+    return out
+
+
+def create_file(path: str, total_bytes: int) -> None:
+    rc = lib().pconv_create_file(os.fsencode(path), total_bytes)
+    if rc != 0:
+        raise OSError(-rc, os.strerror(-rc), path)
+
+
+def write_rect(path: str, row_bytes: int, row0: int, byte0: int, data: np.ndarray) -> None:
+    assert data.dtype == np.uint8 and data.ndim == 2 and data.strides[1] == 1
+    rc = lib().pconv_write_rect(os.fsencode(path), row_bytes, row0, data.shape[0], byte0,
+                                data.shape[1], data.ctypes.data, data.strides[0])
+    if rc != 0:
+        raise OSError(-rc, os.strerror(-rc), path)
+
+
+def synth_rect(seed: int, row_bytes: int, row0: int, nrows: int, byte0: int,
+               nbytes: int) -> np.ndarray:
+    out = np.empty((nrows, nbytes), dtype=np.uint8)
+    lib().pconv_synth_rect(seed & (2**64 - 1), row_bytes, row0, nrows, byte0, nbytes,
+                           out.ctypes.data, out.strides[0])
+    return out
+
+
+def omp_max_threads() -> int:
+    return int(lib().pconv_omp_max_threads())
