@@ -1,0 +1,199 @@
+// Global <-> shared-memory movement of CTA regions, owner lookup across the 3x3 tile
+// neighbourhood, and the system-scope flag primitives of the in-kernel halo protocol.
+//
+// This is where the halo exchange is *fused* into the stencil kernel: a region row/column that
+// belongs to a neighbouring tile is loaded straight from that tile's buffer through its
+// peer-mapped pointer (NVLink P2P load when the neighbour is another GPU, a plain load when it is a
+// virtual rank on the same device). There is no send side, no packing and no staging copy — the
+// reference needs MPI_Isend/Irecv + MPI_Type_vector for the same job (mpi/mpi_conv.c:80-88,
+// 166-200) and never moves the diagonal cells (defect D1); here corners are just the part of the
+// region that happens to fall into a diagonal neighbour's tile.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pconv_cuda.h"
+#include "stencil_core.cuh"
+
+namespace pconv {
+
+struct SourceSet {
+    const uint8_t* p[9];
+    int64_t pitch[9];
+};
+
+__device__ __forceinline__ int owner_of(int64_t v, const int64_t (&lo)[4]) {
+    return v < lo[1] ? 0 : (v < lo[2] ? 1 : 2);
+}
+
+// One 16-byte chunk of the image starting at global byte column gb of global row gr.
+// Chunks that straddle an ownership boundary / the image edge, or are misaligned in their owner's
+// buffer, are assembled byte by byte; everything else is a single 128-bit load (L2-coherent, L1
+// bypass: the data was written by other CTAs / other GPUs).
+__device__ __forceinline__ uint4 load_chunk(const pconv_geometry_t& g, const SourceSet& s,
+                                            int64_t gr, int64_t gb) {
+    uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    if (gr < 0 || gr >= g.img_rows || gb + 16 <= 0 || gb >= g.img_cb) return z;
+    const int orow = owner_of(gr, g.row_lo);
+    const int64_t lrow = gr - g.row_lo[orow];
+    if (gb >= 0 && gb + 16 <= g.img_cb) {
+        const int oc = owner_of(gb, g.cb_lo);
+        if (owner_of(gb + 15, g.cb_lo) == oc) {
+            const int d = orow * 3 + oc;
+            const uint8_t* base = s.p[d];
+            if (base == nullptr) return z;
+            const uint8_t* a = base + lrow * s.pitch[d] + (gb - g.cb_lo[oc]);
+            if ((reinterpret_cast<uintptr_t>(a) & 15u) == 0)
+                return __ldcg(reinterpret_cast<const uint4*>(a));
+        }
+    }
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int64_t b = gb + t;
+        if (b < 0 || b >= g.img_cb) continue;
+        const int oc = owner_of(b, g.cb_lo);
+        const int d = orow * 3 + oc;
+        const uint8_t* base = s.p[d];
+        if (base == nullptr) continue;
+        const uint32_t v = __ldcg(base + lrow * s.pitch[d] + (b - g.cb_lo[oc]));
+        w[t >> 2] |= v << (8 * (t & 3));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Load region rows [r0,r1) x chunk columns [c0,c1) (16-byte units) into buf (and mirror image-
+// exterior zero rows into buf_b so that both ping-pong buffers hold the zero padding).
+// Region (row i, byte x) <-> image (gr0 + i, gb0 + x).
+__device__ __forceinline__ void load_rect(uint8_t* __restrict__ buf, uint8_t* __restrict__ buf_b,
+                                          const pconv_geometry_t& g, const SourceSet& s,
+                                          int64_t gr0, int64_t gb0, int r0, int r1, int c0, int c1) {
+    const int ncols = c1 - c0;
+    const int total = (r1 - r0) * ncols;
+    uint4* b4 = reinterpret_cast<uint4*>(buf);
+    uint4* bb4 = reinterpret_cast<uint4*>(buf_b);
+    if (ncols == kChunksPerRow) {
+        // full-width: a warp reads one contiguous 512-byte row; 4 rows in flight per thread
+        const int cc = threadIdx.x & 31;
+        const int64_t gb = gb0 + 16 * cc;
+        for (int i = r0 + (threadIdx.x >> 5); i < r1; i += 4 * kWarps) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ii = i + u * kWarps;
+                v[u] = (ii < r1) ? load_chunk(g, s, gr0 + ii, gb) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ii = i + u * kWarps;
+                if (ii < r1) {
+                    b4[ii * kChunksPerRow + cc] = v[u];
+                    const int64_t gr = gr0 + ii;
+                    if (bb4 != nullptr && (gr < 0 || gr >= g.img_rows))
+                        bb4[ii * kChunksPerRow + cc] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+            const int i = r0 + idx / ncols, cc = c0 + idx % ncols;
+            const int64_t gr = gr0 + i;
+            b4[i * kChunksPerRow + cc] = load_chunk(g, s, gr, gb0 + 16 * cc);
+            if (bb4 != nullptr && (gr < 0 || gr >= g.img_rows))
+                bb4[i * kChunksPerRow + cc] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
+// Store region rows [r0,r1) x chunk columns [c0,c1) to my tile (clipped to the tile).
+__device__ __forceinline__ void store_rect(const uint8_t* __restrict__ buf, uint8_t* __restrict__ dst,
+                                           const pconv_geometry_t& g, int64_t gr0, int64_t gb0,
+                                           int r0, int r1, int c0, int c1) {
+    const int ncols = c1 - c0;
+    const int total = (r1 - r0) * ncols;
+    const uint4* b4 = reinterpret_cast<const uint4*>(buf);
+    const int64_t tile_rows = g.row_lo[2] - g.row_lo[1];
+    const int64_t tile_cb = g.cb_lo[2] - g.cb_lo[1];
+    for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+        const int i = r0 + idx / ncols, cc = c0 + idx % ncols;
+        const int64_t lr = gr0 + i - g.row_lo[1];
+        const int64_t lb = gb0 + 16 * cc - g.cb_lo[1];
+        if (lr < 0 || lr >= tile_rows || lb + 16 <= 0 || lb >= tile_cb) continue;
+        const uint4 v = b4[i * kChunksPerRow + cc];
+        uint8_t* a = dst + lr * g.pitch + lb;
+        if (lb >= 0 && lb + 16 <= tile_cb && (reinterpret_cast<uintptr_t>(a) & 15u) == 0) {
+            __stcg(reinterpret_cast<uint4*>(a), v);
+        } else {
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+                if (lb + t >= 0 && lb + t < tile_cb) a[t] = (uint8_t)(w[t >> 2] >> (8 * (t & 3)));
+        }
+    }
+}
+
+// Byte mask of a lane's 16-byte strip: 0xff where the byte lies inside the image.
+__device__ __forceinline__ uint4 column_mask(const pconv_geometry_t& g, int64_t gb0, bool* need) {
+    const int64_t gb = gb0 + 16 * (threadIdx.x & 31);
+    uint32_t m[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int64_t b = gb + 4 * j + t;
+            if (b >= 0 && b < g.img_cb) w |= 0xffu << (8 * t);
+        }
+        m[j] = w;
+    }
+    *need = (gb0 < 0) || (gb0 + kSP > g.img_cb);  // CTA-uniform
+    return make_uint4(m[0], m[1], m[2], m[3]);
+}
+
+// ---- system-scope flags ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_add_acq_rel_gpu(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spin until *flag >= want (epochs are monotonically increasing, wrap-safe compare) or the
+// watchdog fires. Returns the ns spent waiting; on timeout records error 1 in status[0].
+__device__ __forceinline__ uint64_t wait_flag(const uint32_t* flag, uint32_t want,
+                                              uint64_t timeout_ns, uint64_t* status) {
+    if ((int32_t)(ld_acquire_sys(flag) - want) >= 0) return 0;
+    const uint64_t t0 = globaltimer_ns();
+    uint64_t dt = 0;
+    while ((int32_t)(ld_acquire_sys(flag) - want) < 0) {
+        __nanosleep(64);
+        dt = globaltimer_ns() - t0;
+        if (dt > timeout_ns) {
+            if (status) atomicExch(reinterpret_cast<unsigned long long*>(status), 1ull);
+            break;
+        }
+    }
+    return dt;
+}
+
+__device__ __forceinline__ void record_wait(uint64_t* status, uint64_t ns) {
+    if (!status) return;
+    atomicMax(reinterpret_cast<unsigned long long*>(status + 1), (unsigned long long)ns);
+    atomicAdd(reinterpret_cast<unsigned long long*>(status + 2), (unsigned long long)ns);
+    atomicAdd(reinterpret_cast<unsigned long long*>(status + 3), 1ull);
+}
+
+}  // namespace pconv

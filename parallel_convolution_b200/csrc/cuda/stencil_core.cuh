@@ -1,0 +1,388 @@
+// Device-side stencil core shared by the streaming and the resident kernels.
+//
+// Geometry (all kernels): a CTA of 512 threads (16 warps) owns a shared-memory *region* of RH rows
+// x 512 bytes (kSP). One warp spans the full region width: lane l owns the 16-byte strip
+// [16 l, 16 l + 16) of every row it works on, so the row loads/stores are conflict-free LDS.128 /
+// STS.128 and horizontal neighbours that fall outside a lane's strip come from the adjacent lane
+// with warp shuffles (never from shared memory). Warps split the rows of an iteration into 16
+// contiguous segments and *stream* down their segment: pushing input row r+1 completes output
+// row r. k iterations are fused per region (temporal blocking): iteration j recomputes
+// rows [j, RH-j) of the region, the outer ring goes stale by one pixel per iteration and the halo
+// (k rows, HB >= k*C bytes) absorbs it, so results are bit-identical to k global passes.
+//
+// An interleaved image is a byte stream whose horizontal neighbour is C bytes away (C = 1 grey,
+// 3 RGB): grey and RGB share every line of code below except the lane-shuffle patterns.
+//
+// Arithmetic paths (selected by the host-side classifier, csrc/host/filters.cpp; each is
+// bit-identical to the fp32 oracle of csrc/host/oracle.cpp for the filters routed to it):
+//   Sep121Path : [1 2 1]x[1 2 1]/16, 16-bit SWAR lanes, vertical pass first       ~15 ALU ops / 4 B
+//   IntPath    : any integer taps, divisor 2^s, biased 16-bit SWAR IMAD lanes     ~30 ALU ops / 4 B
+//   F32Path    : any fp32 taps, __fmul_rn/__fadd_rn in the oracle's tap order     ~20 ALU ops / B
+// (Reference kernels for contrast: one thread per pixel, 9-27 scalar byte loads and FP64 DFMAs,
+//  cuda/cuda_convolute.cu:9-47.)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../common/pconv_types.h"
+
+namespace pconv {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kSP = 512;            // region width == smem row pitch, bytes
+constexpr int kChunksPerRow = kSP / 16;  // 32 == one 16-byte chunk per lane
+constexpr unsigned kFull = 0xffffffffu;
+
+// Device copy of the filter with the constants the epilogues need (built by the launcher).
+struct FilterDev {
+    float h[9];
+    int32_t w[9];
+    int32_t shift;
+    uint32_t bias2;     // IntPath: (bias << 16) | bias, bias = -S_min
+    uint32_t negbias2;  // IntPath: packed (-bias) as s16x2
+    uint32_t maxv2;     // IntPath: packed ((256 << shift) - 1)
+    int32_t clamp_lo;   // result can go negative  -> clamp at 0
+    int32_t clamp_hi;   // result can exceed 255   -> clamp at 255
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
+    return __byte_perm(a, b, s);
+}
+// packed signed 16-bit lane arithmetic (PTX ISA 8.0, sm_90+; native on sm_100a)
+__device__ __forceinline__ uint32_t add_s16x2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t min_s16x2_relu(uint32_t a, uint32_t b) {  // max(min(a,b),0)
+    uint32_t r;
+    asm("min.s16x2.relu %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+// 16-bit lanes: E = bytes (2,0) of a word, O = bytes (3,1); value in the low byte of each lane.
+__device__ __forceinline__ uint32_t lanes_even(uint32_t w) { return w & 0x00ff00ffu; }
+__device__ __forceinline__ uint32_t lanes_odd(uint32_t w) { return prmt(w, 0u, 0x4341u); }
+// (hi lane of a) -> lo lane, (lo lane of b) -> hi lane: "the next 16-bit lane pair to the right".
+__device__ __forceinline__ uint32_t lanes_shift(uint32_t a, uint32_t b) { return prmt(a, b, 0x5432u); }
+
+// =============================================================================================
+// Sep121Path — the reference's default Gaussian (mpi/mpi_conv.c:96,104; cuda_convolute.cu:12).
+// Exactness: every partial sum is an integer <= 4080 < 2^16, result = sum >> 4.
+//   vertical   V_r(x)  = p_{r-1}(x) + 2 p_r(x) + p_{r+1}(x)  as (U_{r-1}+U_r) + (U_r+U_{r+1})
+//   horizontal out(x)  = V(x-C) + 2 V(x) + V(x+C)            as  s(x-C) + s(x),  s(x) = V(x)+V(x+C)
+// =============================================================================================
+template <int C>
+struct Sep121Path {
+    static_assert(C == 1 || C == 3, "channel strides 1 (grey) and 3 (RGB) are implemented");
+    uint32_t uE[4], uO[4];  // unpacked lanes of the last pushed row
+    uint32_t pE[4], pO[4];  // pair sum U_{r-1} + U_r
+
+    __device__ __forceinline__ Sep121Path(const FilterDev&) {}
+
+    // first row of a segment (row a-1): nothing to emit, nothing to accumulate yet
+    __device__ __forceinline__ void prime0(const uint4& w) {
+        const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { uE[j] = lanes_even(x[j]); uO[j] = lanes_odd(x[j]); }
+    }
+    // second row (row a)
+    __device__ __forceinline__ void prime1(const uint4& w) {
+        const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t nE = lanes_even(x[j]), nO = lanes_odd(x[j]);
+            pE[j] = uE[j] + nE; pO[j] = uO[j] + nO;
+            uE[j] = nE; uO[j] = nO;
+        }
+    }
+    // push row r+1, return output row r
+    __device__ __forceinline__ uint4 push(const uint4& w) {
+        const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+        uint32_t vE[5], vO[5];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t nE = lanes_even(x[j]), nO = lanes_odd(x[j]);
+            const uint32_t qE = uE[j] + nE, qO = uO[j] + nO;  // U_r + U_{r+1}
+            vE[j] = pE[j] + qE; vO[j] = pO[j] + qO;           // V_r  (<= 1020 per lane)
+            pE[j] = qE; pO[j] = qO; uE[j] = nE; uO[j] = nO;
+        }
+        uint32_t o[4];
+        if (C == 1) {
+            vE[4] = __shfl_down_sync(kFull, vE[0], 1);  // right neighbour's first even lanes
+            uint32_t so[5];                              // so[j+1] = SO_j = (s(4j+3), s(4j+1))
+#pragma unroll
+            for (int j = 0; j < 4; ++j) so[j + 1] = vO[j] + lanes_shift(vE[j], vE[j + 1]);
+            so[0] = __shfl_up_sync(kFull, so[4], 1);    // left neighbour's last SO
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t se = vE[j] + vO[j];                       // (s(4j+2), s(4j))
+                const uint32_t oE = se + lanes_shift(so[j], so[j + 1]);  // s(x-1) + s(x), even x
+                const uint32_t oO = se + so[j + 1];                      // odd x
+                o[j] = ((oE >> 4) & 0x00ff00ffu) | ((oO << 4) & 0xff00ff00u);
+            }
+        } else {
+            vE[4] = __shfl_down_sync(kFull, vE[0], 1);
+            vO[4] = __shfl_down_sync(kFull, vO[0], 1);
+            uint32_t se[5], so[5];  // index j+1 holds word j; index 0 is the left neighbour's word 3
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                se[j + 1] = vE[j] + lanes_shift(vO[j], vO[j + 1]);  // (s3(4j+2), s3(4j))
+                so[j + 1] = vO[j] + vE[j + 1];                      // (s3(4j+3), s3(4j+1))
+            }
+            se[0] = __shfl_up_sync(kFull, se[4], 1);
+            so[0] = __shfl_up_sync(kFull, so[4], 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t oE = se[j + 1] + so[j];                           // s3(x-3)+s3(x), even x
+                const uint32_t oO = so[j + 1] + lanes_shift(se[j], se[j + 1]);   // odd x
+                o[j] = ((oE >> 4) & 0x00ff00ffu) | ((oO << 4) & 0xff00ff00u);
+            }
+        }
+        return make_uint4(o[0], o[1], o[2], o[3]);
+    }
+};
+
+// =============================================================================================
+// IntPath — arbitrary integer taps over 2^shift (sharpen, laplacian, emboss, sobel, ...).
+// Scatter form: input row r+1 contributes taps k=2 to output row r, k=1 to row r+1, k=0 to row
+// r+2; three rotating accumulators per 16-bit lane pair. Negative taps are handled by running
+// the 32-bit IMAD on both lanes at once: inter-lane borrows cancel mod 2^32 as long as each final
+// lane total is in [0, 65535], which the bias guarantees (bias = -S_min, bias + S_max <= 32767).
+// =============================================================================================
+template <int C>
+struct IntPath {
+    static_assert(C == 1 || C == 3, "channel strides 1 (grey) and 3 (RGB) are implemented");
+    uint32_t aE[3][4], aO[3][4];  // [slot][word]; slot roles rotate with the row phase
+    const FilterDev& f;
+
+    __device__ __forceinline__ IntPath(const FilterDev& fd) : f(fd) {}
+
+    template <int K>
+    __device__ __forceinline__ void tap_row(uint32_t (&accE)[4], uint32_t (&accO)[4],
+                                            const uint32_t (&E)[6], const uint32_t (&O)[6],
+                                            bool fresh) {
+        // E/O index: 0 = left neighbour's word 3, 1..4 = own words, 5 = right neighbour's word 0
+        const uint32_t wl = (uint32_t)f.w[3 * K + 0], wc = (uint32_t)f.w[3 * K + 1],
+                       wr = (uint32_t)f.w[3 * K + 2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t lE, rE, lO, rO;  // lanes at x-C / x+C for the even / odd positions of word j
+            if (C == 1) {
+                lE = lanes_shift(O[j], O[j + 1]); rE = O[j + 1];
+                lO = E[j + 1];                    rO = lanes_shift(E[j + 1], E[j + 2]);
+            } else {
+                lE = O[j];                        rE = lanes_shift(O[j + 1], O[j + 2]);
+                lO = lanes_shift(E[j], E[j + 1]); rO = E[j + 2];
+            }
+            uint32_t e = fresh ? f.bias2 : accE[j];
+            uint32_t o = fresh ? f.bias2 : accO[j];
+            if (wl) { e += wl * lE; o += wl * lO; }
+            if (wc) { e += wc * E[j + 1]; o += wc * O[j + 1]; }
+            if (wr) { e += wr * rE; o += wr * rO; }
+            accE[j] = e; accO[j] = o;
+        }
+    }
+
+    __device__ __forceinline__ void unpack(const uint4& w, uint32_t (&E)[6], uint32_t (&O)[6]) {
+        const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+        const uint32_t xl = __shfl_up_sync(kFull, w.w, 1);    // left neighbour's last word
+        const uint32_t xr = __shfl_down_sync(kFull, w.x, 1);  // right neighbour's first word
+        E[0] = lanes_even(xl); O[0] = lanes_odd(xl);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { E[j + 1] = lanes_even(x[j]); O[j + 1] = lanes_odd(x[j]); }
+        E[5] = lanes_even(xr); O[5] = lanes_odd(xr);
+    }
+
+    // PH = row phase (0,1,2): slot PH is completed by this row, (PH+1)%3 gets k=1, (PH+2)%3 k=0.
+    template <int PH>
+    __device__ __forceinline__ void prime0(const uint4& w) {  // row a-1: only k=0 -> out row a
+        uint32_t E[6], O[6];
+        unpack(w, E, O);
+        tap_row<0>(aE[(PH + 2) % 3], aO[(PH + 2) % 3], E, O, true);
+    }
+    template <int PH>
+    __device__ __forceinline__ void prime1(const uint4& w) {  // row a: k=1 -> a, k=0 -> a+1
+        uint32_t E[6], O[6];
+        unpack(w, E, O);
+        tap_row<1>(aE[(PH + 1) % 3], aO[(PH + 1) % 3], E, O, false);
+        tap_row<0>(aE[(PH + 2) % 3], aO[(PH + 2) % 3], E, O, true);
+    }
+    template <int PH>
+    __device__ __forceinline__ uint4 push(const uint4& w) {
+        uint32_t E[6], O[6];
+        unpack(w, E, O);
+        tap_row<2>(aE[PH], aO[PH], E, O, false);
+        tap_row<1>(aE[(PH + 1) % 3], aO[(PH + 1) % 3], E, O, false);
+        tap_row<0>(aE[(PH + 2) % 3], aO[(PH + 2) % 3], E, O, true);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t e = aE[PH][j], q = aO[PH][j];
+            // per 16-bit lane: clamp(acc - bias, 0, (256<<s)-1) in two packed ops (sm_90+ s16x2 ISA)
+            e = min_s16x2_relu(add_s16x2(e, f.negbias2), f.maxv2);
+            q = min_s16x2_relu(add_s16x2(q, f.negbias2), f.maxv2);
+            e >>= f.shift; q >>= f.shift;  // lane-crossing bits land in byte 1/3, never selected
+            o[j] = prmt(e, q, 0x6240u);
+        }
+        return make_uint4(o[0], o[1], o[2], o[3]);
+    }
+};
+
+// =============================================================================================
+// F32Path — exact emulation of the oracle's fp32 sequence for arbitrary taps (box/9, edge/28,
+// user floats). Scatter form keeps the oracle's order: row r-1 adds taps (0,0),(0,1),(0,2) to
+// output row r first, then row r adds (1,*), then row r+1 adds (2,*). mul and add are separately
+// rounded (__fmul_rn/__fadd_rn: never contracted to FMA). Truncation uses the 2^23 trick with a
+// round-toward-zero add. (The reference's GPU kernel promotes every tap to FP64,
+// cuda/cuda_convolute.cu:21,38-40; that is only exact for /16.)
+// =============================================================================================
+template <int C>
+struct F32Path {
+    static_assert(C == 1 || C == 3, "channel strides 1 (grey) and 3 (RGB) are implemented");
+    float acc[3][16];
+    const FilterDev& f;
+
+    __device__ __forceinline__ F32Path(const FilterDev& fd) : f(fd) {}
+
+    __device__ __forceinline__ static float byte_to_float(uint32_t w, int i) {
+        // place byte i in the low mantissa bits of 2^23, subtract 2^23: exact u8 -> f32 in 2 ops
+        return __uint_as_float(prmt(w, 0x4b000000u, 0x7650u | (uint32_t)i)) - 8388608.0f;
+    }
+
+    // v index: 0..C-1 = left neighbour's last C bytes, C..C+15 = own bytes, then C right bytes
+    __device__ __forceinline__ void convert(const uint4& w, float (&v)[16 + 2 * C]) {
+        const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+        const uint32_t xl = __shfl_up_sync(kFull, w.w, 1);
+        const uint32_t xr = __shfl_down_sync(kFull, w.x, 1);
+#pragma unroll
+        for (int i = 0; i < C; ++i) v[i] = byte_to_float(xl, 4 - C + i);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[C + i] = byte_to_float(x[i >> 2], i & 3);
+#pragma unroll
+        for (int i = 0; i < C; ++i) v[C + 16 + i] = byte_to_float(xr, i);
+    }
+
+    template <int K>
+    __device__ __forceinline__ void tap_row(float (&a)[16], const float (&v)[16 + 2 * C], bool fresh) {
+        const float hl = f.h[3 * K], hc = f.h[3 * K + 1], hr = f.h[3 * K + 2];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float ql = __fmul_rn(v[i], hl);             // byte at x - C
+            const float qc = __fmul_rn(v[i + C], hc);         // x
+            const float qr = __fmul_rn(v[i + 2 * C], hr);     // x + C
+            float s = fresh ? ql : __fadd_rn(a[i], ql);       // 0 + q == q (sign of zero is moot)
+            s = __fadd_rn(s, qc);
+            a[i] = __fadd_rn(s, qr);
+        }
+    }
+
+    template <int PH>
+    __device__ __forceinline__ void prime0(const uint4& w) {
+        float v[16 + 2 * C];
+        convert(w, v);
+        tap_row<0>(acc[(PH + 2) % 3], v, true);
+    }
+    template <int PH>
+    __device__ __forceinline__ void prime1(const uint4& w) {
+        float v[16 + 2 * C];
+        convert(w, v);
+        tap_row<1>(acc[(PH + 1) % 3], v, false);
+        tap_row<0>(acc[(PH + 2) % 3], v, true);
+    }
+    template <int PH>
+    __device__ __forceinline__ uint4 push(const uint4& w) {
+        float v[16 + 2 * C];
+        convert(w, v);
+        tap_row<2>(acc[PH], v, false);
+        tap_row<1>(acc[(PH + 1) % 3], v, false);
+        tap_row<0>(acc[(PH + 2) % 3], v, true);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t t[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                float s = acc[PH][4 * j + b];
+                if (f.clamp_lo) s = fmaxf(s, 0.0f);
+                if (f.clamp_hi) s = fminf(s, 255.0f);
+                t[b] = __float_as_uint(__fadd_rz(s, 8388608.0f));  // low byte = trunc(s)
+            }
+            o[j] = prmt(prmt(t[0], t[1], 0x0040u), prmt(t[2], t[3], 0x0040u), 0x5410u);
+        }
+        return make_uint4(o[0], o[1], o[2], o[3]);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// One fused iteration over region rows [lo, hi) (1 <= lo, hi <= RH-1): s_src -> s_dst.
+// mask[j] clears output bytes that lie outside the image (zero padding must stay zero).
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void iterate_sep121(const uint8_t* __restrict__ s_src,
+                                               uint8_t* __restrict__ s_dst, int lo, int hi,
+                                               const uint4& mask, bool need_mask,
+                                               const FilterDev& f) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = (hi - lo + kWarps - 1) / kWarps;
+    const int a = lo + warp * seg;
+    const int b = min(a + seg, hi);
+    if (a >= b) return;  // warp-uniform
+    const uint4* src = reinterpret_cast<const uint4*>(s_src) + lane;
+    uint4* dst = reinterpret_cast<uint4*>(s_dst) + lane;
+    Sep121Path<C> p(f);
+    p.prime0(src[(a - 1) * kChunksPerRow]);
+    p.prime1(src[a * kChunksPerRow]);
+    uint4 nxt = src[(a + 1) * kChunksPerRow];
+#pragma unroll 2
+    for (int r = a; r < b; ++r) {
+        const uint4 cur = nxt;
+        if (r + 1 < b) nxt = src[(r + 2) * kChunksPerRow];  // software prefetch (r+2 <= RH-1)
+        uint4 o = p.push(cur);
+        if (need_mask) { o.x &= mask.x; o.y &= mask.y; o.z &= mask.z; o.w &= mask.w; }
+        dst[r * kChunksPerRow] = o;
+    }
+}
+
+template <template <int> class Path, int C>
+__device__ __forceinline__ void iterate_phased(const uint8_t* __restrict__ s_src,
+                                               uint8_t* __restrict__ s_dst, int lo, int hi,
+                                               const uint4& mask, bool need_mask,
+                                               const FilterDev& f) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = (hi - lo + kWarps - 1) / kWarps;
+    const int a = lo + warp * seg;
+    const int b = min(a + seg, hi);
+    if (a >= b) return;
+    const uint4* src = reinterpret_cast<const uint4*>(s_src) + lane;
+    uint4* dst = reinterpret_cast<uint4*>(s_dst) + lane;
+    Path<C> p(f);
+    // priming rows behave like pushes with phases -2 and -1 (== 1 and 2 mod 3)
+    p.template prime0<1>(src[(a - 1) * kChunksPerRow]);
+    p.template prime1<2>(src[a * kChunksPerRow]);
+    auto emit = [&](int r, uint4 o) {
+        if (need_mask) { o.x &= mask.x; o.y &= mask.y; o.z &= mask.z; o.w &= mask.w; }
+        dst[r * kChunksPerRow] = o;
+    };
+    int r = a;
+    for (; r + 2 < b; r += 3) {  // phases rotate the accumulator roles without register moves
+        emit(r, p.template push<0>(src[(r + 1) * kChunksPerRow]));
+        emit(r + 1, p.template push<1>(src[(r + 2) * kChunksPerRow]));
+        emit(r + 2, p.template push<2>(src[(r + 3) * kChunksPerRow]));
+    }
+    if (r < b) emit(r, p.template push<0>(src[(r + 1) * kChunksPerRow]));
+    if (r + 1 < b) emit(r + 1, p.template push<1>(src[(r + 2) * kChunksPerRow]));
+}
+
+template <int KIND, int C>
+__device__ __forceinline__ void iterate_region(const uint8_t* __restrict__ s_src,
+                                               uint8_t* __restrict__ s_dst, int lo, int hi,
+                                               const uint4& mask, bool need_mask,
+                                               const FilterDev& f) {
+    if (KIND == PCONV_KIND_SEP121) iterate_sep121<C>(s_src, s_dst, lo, hi, mask, need_mask, f);
+    else if (KIND == PCONV_KIND_INT) iterate_phased<IntPath, C>(s_src, s_dst, lo, hi, mask, need_mask, f);
+    else iterate_phased<F32Path, C>(s_src, s_dst, lo, hi, mask, need_mask, f);
+}
+
+}  // namespace pconv

@@ -1,0 +1,269 @@
+"""Fused stencil + halo backend (the product): drives ``stream_kernel`` / ``resident_kernel``.
+
+One *tile driver* per rank owns two ping-pong tile buffers, a flag pad and a status block in
+plain ``cudaMalloc`` memory (IPC-exportable, see ``peer_memory.py``). A launch gets the base
+pointers of the up-to-eight neighbouring tiles; the kernel pulls halo rows / columns / corners
+straight out of those buffers (NVLink P2P loads across GPUs) and synchronises with per-launch
+epoch flags written by the neighbours with ``st.release.sys``. There is no NCCL and no host
+round trip on this path; the host enqueues every launch of a run up front.
+
+Replaces the reference's ``MPI_Isend/Irecv`` + ``MPI_Wait`` iteration loop
+(``mpi/mpi_conv.c:164-248``) for the GPU path.
+
+``VirtualCluster`` runs N tile drivers on ONE device in one process (peer pointers degenerate to
+local pointers) — the way multi-GPU logic is tested on a 1-GPU box.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from ..models.filters import Filter
+from ..ops import cuda as K
+from .decomposition import TileGrid
+from .plan import StreamPlan, plan_stream
+
+FLAG_BYTES = 256      # 9 x u32 flags + padding
+STATUS_WORDS = 4      # u64: error, max wait ns, sum wait ns, waits
+
+
+def tile_pitch(grid: TileGrid) -> int:
+    """Common byte pitch of every tile buffer: widest tile rounded up to 128 B."""
+    cb = grid.max_tile_cols() * grid.channels
+    return (cb + 127) // 128 * 128
+
+
+@dataclass
+class RankMemory:
+    """Device memory of one rank. ``owned`` is False for peer-mapped views of another rank."""
+
+    bufs: list[int]
+    flags: int
+    counter: int = 0
+    status: int = 0
+    nbytes: int = 0
+    owned: bool = True
+
+    @staticmethod
+    def allocate(rows: int, pitch: int) -> "RankMemory":
+        nbytes = rows * pitch + 256
+        bufs = [K.malloc(nbytes), K.malloc(nbytes)]
+        ctl = K.malloc(FLAG_BYTES + 64 + 8 * STATUS_WORDS + 64)
+        return RankMemory(bufs, ctl, ctl + FLAG_BYTES, ctl + FLAG_BYTES + 64, nbytes, True)
+
+    def free(self) -> None:
+        if self.owned:
+            for p in self.bufs:
+                K.free(p)
+            K.free(self.flags)
+        self.bufs, self.flags = [], 0
+
+
+@dataclass
+class RunStats:
+    launches: int = 0
+    watchdog: bool = False
+    max_wait_us: float = 0.0
+    sum_wait_us: float = 0.0
+    waits: int = 0
+    plan: StreamPlan | None = None
+
+
+class TileDriver:
+    """Enqueues the fused kernel launches for one tile."""
+
+    def __init__(self, grid: TileGrid, rank: int, filt: Filter, mem: RankMemory,
+                 neighbors: list[RankMemory | None], pitch: int, stream: int = 0,
+                 timeout_ms: float = 10_000.0):
+        self.grid, self.rank, self.filt, self.mem = grid, rank, filt, mem
+        self.neighbors = neighbors          # 9 entries, index 4 = self.mem
+        self.pitch, self.stream = pitch, stream
+        self.timeout_ns = int(timeout_ms * 1e6)
+        self.tile = grid.tile(rank)
+        self.epoch = 0                      # last epoch signalled
+        self.inject_delay_ns = 0            # fault injection (tests / --inject-*)
+        self.inject_drop_signal = False
+        self._geom = self._geometry()
+
+    # -- geometry ---------------------------------------------------------------------------
+    def _geometry(self) -> K.Geometry:
+        g, t = self.grid, self.tile
+        rb, cbn = g.row_bounds(), g.col_bounds()
+        Cn = g.channels
+
+        def window(bounds: list[int], i: int, n: int) -> list[int]:
+            lo_prev = bounds[i - 1] if i > 0 else bounds[i]
+            hi_next = bounds[i + 2] if i + 1 < n else bounds[i + 1]
+            return [lo_prev, bounds[i], bounds[i + 1], hi_next]
+
+        geo = K.Geometry()
+        geo.img_rows, geo.img_cb = g.height, g.width * Cn
+        geo.row_lo = (C.c_int64 * 4)(*window(rb, t.ty, g.grid_rows))
+        geo.cb_lo = (C.c_int64 * 4)(*[v * Cn for v in window(cbn, t.tx, g.grid_cols)])
+        geo.pitch, geo.C = self.pitch, Cn
+        return geo
+
+    # -- launches ---------------------------------------------------------------------------
+    def _params(self, plan: StreamPlan, k: int, src_parity: int, wait: int, signal: int,
+                grid_ctas: int = 0) -> K.StreamParams:
+        p = K.StreamParams()
+        p.g = self._geom
+        for d in range(9):
+            nb = self.neighbors[d]
+            p.src[d] = nb.bufs[src_parity] if nb is not None else None
+            p.src_pitch[d] = self.pitch
+            p.sync.remote_flags[d] = (nb.flags + 4 * (8 - d)) if (nb is not None and d != 4) else None
+        p.dst = self.mem.bufs[src_parity ^ 1]
+        p.filt = self.filt.spec
+        p.k, p.TH, p.TWB, p.HB, p.grid = k, plan.TH, plan.TWB, plan.HB, grid_ctas
+        # (a shallower tail launch, k < plan.k, keeps TH/HB: HB >= k*C still holds and RH shrinks)
+        p.sync.local_flags = self.mem.flags
+        p.sync.done_counter = self.mem.counter
+        p.sync.status = self.mem.status
+        p.sync.wait_value, p.sync.signal_value = wait, signal
+        p.sync.timeout_ns = self.timeout_ns
+        p.sync.inject_delay_ns = self.inject_delay_ns
+        p.sync.inject_drop_signal = 1 if self.inject_drop_signal else 0
+        return p
+
+    def enqueue(self, plan: StreamPlan, k: int, src_parity: int, first: bool,
+                multi: bool) -> None:
+        """One launch of ``k`` fused iterations reading ``bufs[src_parity]``."""
+        if multi:
+            self.epoch += 1
+            wait = 0 if first else self.epoch - 1
+            signal = self.epoch
+        else:
+            wait = signal = 0
+        K.stream_launch(self._params(plan, k, src_parity, wait, signal), self.stream)
+
+    # -- data movement ----------------------------------------------------------------------
+    def upload(self, tile: np.ndarray, parity: int = 0) -> None:
+        t = self.tile
+        cb = t.cols * self.grid.channels
+        arr = np.ascontiguousarray(tile, dtype=np.uint8).reshape(t.rows, cb)
+        K.memcpy2d_async(self.mem.bufs[parity], self.pitch, arr.ctypes.data, cb, cb, t.rows,
+                         K.H2D, self.stream)
+        K.stream_sync(self.stream)  # arr may be a temporary
+
+    def download(self, parity: int) -> np.ndarray:
+        t = self.tile
+        cb = t.cols * self.grid.channels
+        out = np.empty((t.rows, cb), dtype=np.uint8)
+        K.memcpy2d_async(out.ctypes.data, cb, self.mem.bufs[parity], self.pitch, cb, t.rows,
+                         K.D2H, self.stream)
+        K.stream_sync(self.stream)
+        return out
+
+    def synth(self, seed: int, parity: int = 0) -> None:
+        t, Cn = self.tile, self.grid.channels
+        K.synth_rect(seed, self.grid.row_bytes, t.row0, t.rows, t.col0 * Cn, t.cols * Cn,
+                     self.mem.bufs[parity], self.pitch, self.stream)
+
+    def reset_status(self) -> None:
+        K.memset_async(self.mem.status, 0, 8 * STATUS_WORDS, self.stream)
+
+    def read_status(self) -> tuple[bool, float, float, int]:
+        out = np.zeros(STATUS_WORDS, dtype=np.uint64)
+        K.memcpy_async(out.ctypes.data, self.mem.status, 8 * STATUS_WORDS, K.D2H, self.stream)
+        K.stream_sync(self.stream)
+        return bool(out[0]), float(out[1]) / 1e3, float(out[2]) / 1e3, int(out[3])
+
+
+def make_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int | None = None,
+              sms: int | None = None, max_rh: int | None = None) -> StreamPlan:
+    """The (rank-independent) stream plan for a grid."""
+    Cn = grid.channels
+    multi_r, multi_c = grid.grid_rows > 1, grid.grid_cols > 1
+    kw = {}
+    if sms:
+        kw["sms"] = sms
+    if max_rh:
+        kw["max_rh"] = max_rh
+    return plan_stream(grid.max_tile_rows(), grid.max_tile_cols() * Cn, Cn, filt.kind,
+                       max(loops, 1),
+                       min_nbr_rows=grid.min_tile_rows() if multi_r else None,
+                       min_nbr_cols=grid.min_tile_cols() if multi_c else None,
+                       force_k=halo_depth, **kw)
+
+
+class VirtualCluster:
+    """N tiles on one device in one process; launches are interleaved rank by rank on one stream.
+
+    The kernels, flag protocol and owner lookup are exactly the multi-GPU ones; only the pointers
+    are local. Used by the tests and by ``ConvEngine(workers=N)`` on a single GPU.
+    """
+
+    def __init__(self, grid: TileGrid, filt: Filter, stream: int = 0,
+                 halo_depth: int | None = None, use_flags: bool = True):
+        self.grid, self.filt, self.stream = grid, filt, stream
+        self.halo_depth, self.use_flags = halo_depth, use_flags
+        self.pitch = tile_pitch(grid)
+        rows = grid.max_tile_rows()
+        self.mems = [RankMemory.allocate(rows, self.pitch) for _ in range(grid.workers)]
+        self.drivers: list[TileDriver] = []
+        for r in range(grid.workers):
+            nbrs = [self.mems[n] if n >= 0 else None for n in grid.neighbors(r)]
+            self.drivers.append(TileDriver(grid, r, filt, self.mems[r], nbrs, self.pitch, stream))
+        self.sms = K.sm_count()
+        self.max_rh = K.max_region_rows(1)
+        self.parity = 0
+        self.last = RunStats()
+
+    def close(self) -> None:
+        for m in self.mems:
+            m.free()
+        self.mems = []
+
+    def upload(self, image: np.ndarray) -> None:
+        g = self.grid
+        img = np.ascontiguousarray(image, dtype=np.uint8).reshape(g.height, g.row_bytes)
+        for d in self.drivers:
+            t = d.tile
+            d.upload(img[t.row0:t.row0 + t.rows, t.col0 * g.channels:(t.col0 + t.cols) * g.channels], 0)
+        self.parity = 0
+
+    def synth(self, seed: int) -> None:
+        for d in self.drivers:
+            d.synth(seed, 0)
+        self.parity = 0
+
+    def download(self) -> np.ndarray:
+        g = self.grid
+        out = np.empty((g.height, g.row_bytes), dtype=np.uint8)
+        for d in self.drivers:
+            t = d.tile
+            out[t.row0:t.row0 + t.rows, t.col0 * g.channels:(t.col0 + t.cols) * g.channels] = \
+                d.download(self.parity)
+        return out
+
+    def run(self, loops: int, plan: StreamPlan | None = None) -> RunStats:
+        """Enqueue ``loops`` iterations (asynchronous; ``download`` synchronises)."""
+        stats = RunStats()
+        if loops <= 0:
+            self.last = stats
+            return stats
+        plan = plan or make_plan(self.grid, self.filt, loops, self.halo_depth, self.sms, self.max_rh)
+        stats.plan = plan
+        multi = self.use_flags and self.grid.workers > 1
+        for d in self.drivers:
+            d.reset_status()
+        for i, k in enumerate(plan.launches(loops)):
+            for d in self.drivers:
+                d.enqueue(plan, k, self.parity, first=(i == 0), multi=multi)
+            self.parity ^= 1
+            stats.launches += len(self.drivers)
+        self.last = stats
+        return stats
+
+    def collect_status(self) -> RunStats:
+        s = self.last
+        for d in self.drivers:
+            err, mx, sm, n = d.read_status()
+            s.watchdog |= err
+            s.max_wait_us = max(s.max_wait_us, mx)
+            s.sum_wait_us += sm
+            s.waits += n
+        return s

@@ -1,0 +1,50 @@
+"""Quick device-timed throughput probe (development aid; bench.py is the judged harness)."""
+import argparse
+import json
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from parallel_convolution_b200.models.filters import Filter
+from parallel_convolution_b200.ops import cuda as K
+from parallel_convolution_b200.parallel.decomposition import TileGrid
+from parallel_convolution_b200.parallel.fused import VirtualCluster, make_plan
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=2520)
+    ap.add_argument("--channels", type=int, default=3)
+    ap.add_argument("--loops", type=int, default=100)
+    ap.add_argument("--filter", default="gaussian")
+    ap.add_argument("--workers", type=int, default=1)
+    ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--reps", type=int, default=5)
+    a = ap.parse_args()
+    f = Filter.parse(a.filter)
+    g = TileGrid.create(a.height, a.width, a.channels, a.workers)
+    vc = VirtualCluster(g, f, halo_depth=a.k or None)
+    vc.synth(1)
+    plan = make_plan(g, f, a.loops, a.k or None, vc.sms, vc.max_rh)
+    vc.run(a.loops, plan)
+    K.device_sync()
+    best = 1e9
+    for _ in range(a.reps):
+        e0, e1 = K.Event(), K.Event()
+        e0.record(0)
+        vc.run(a.loops, plan)
+        e1.record(0)
+        e1.synchronize()
+        best = min(best, e0.elapsed_ms(e1))
+    mpx = a.width * a.height * a.loops / (best * 1e-3) / 1e6
+    print(json.dumps({"shape": [a.height, a.width, a.channels], "filter": f.name, "path": f.kind_name,
+                      "loops": a.loops, "workers": a.workers, "plan": plan.__dict__,
+                      "ms": round(best, 4), "mpx_s": round(mpx, 1),
+                      "us_per_iter": round(best * 1e3 / a.loops, 3)}))
+    vc.close()
+
+
+if __name__ == "__main__":
+    main()
