@@ -50,17 +50,17 @@ typedef struct pconv_stream_params {
     uint8_t* dst;            // my destination tile (pitch g.pitch)
     pconv_filter_t filt;
     int32_t k;               // fused iterations in this launch (>= 1)
-    int32_t TH;              // interior rows per CTA region
+    int32_t TH;              // interior rows per CTA region (TH + 2k <= 16*R)
     int32_t TWB;             // interior bytes per CTA region (multiple of 16, <= 512 - 2*HB)
     int32_t HB;              // column halo bytes (multiple of 16, >= k*C)
-    int32_t grid;            // CTAs to launch (0: one per SM x occupancy)
-    int32_t pad_;
+    int32_t grid;            // CTAs to launch (0: one per SM)
+    int32_t R;               // band height: rows per warp held in registers (region = 16*R rows)
     pconv_sync_t sync;
 } pconv_stream_params_t;
 
 int pconv_stream_launch(const pconv_stream_params_t* p, void* stream);
-// Max region rows RH = TH + 2k that fit in shared memory for `ctas_per_sm` co-resident CTAs.
-int pconv_stream_max_region_rows(int ctas_per_sm);
+// Band heights compiled for a filter kind; returns the count, fills out[0..cap).
+int pconv_stream_band_heights(int kind, int* out, int cap);
 
 // ---- resident kernel: the whole tile stays in shared memory for all iterations -----------------
 typedef struct pconv_resident_params {

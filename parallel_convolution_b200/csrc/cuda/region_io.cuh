@@ -27,13 +27,31 @@ __device__ __forceinline__ int owner_of(int64_t v, const int64_t (&lo)[4]) {
     return v < lo[1] ? 0 : (v < lo[2] ? 1 : 2);
 }
 
-// One 16-byte chunk of the image starting at global byte column gb of global row gr.
-// Chunks that straddle an ownership boundary / the image edge, or are misaligned in their owner's
-// buffer, are assembled byte by byte; everything else is a single 128-bit load (L2-coherent, L1
-// bypass: the data was written by other CTAs / other GPUs).
+// Slow path of load_chunk: a chunk that straddles an ownership boundary / the image edge, or is
+// misaligned in its owner's buffer, is assembled byte by byte. Kept out of line: it is rare (only
+// odd tile widths hit it) and would otherwise be unrolled into every band row.
+__device__ __noinline__ uint4 load_chunk_bytes(const pconv_geometry_t& g, const SourceSet& s,
+                                               int orow, int64_t lrow, int64_t gb) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    for (int t = 0; t < 16; ++t) {
+        const int64_t b = gb + t;
+        if (b < 0 || b >= g.img_cb) continue;
+        const int oc = owner_of(b, g.cb_lo);
+        const int d = orow * 3 + oc;
+        const uint8_t* base = s.p[d];
+        if (base == nullptr) continue;
+        const uint32_t v = __ldcg(base + lrow * s.pitch[d] + (b - g.cb_lo[oc]));
+        w[t >> 2] |= v << (8 * (t & 3));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// One 16-byte chunk of the image starting at global byte column gb of global row gr: a single
+// 128-bit load through the owning tile's (possibly peer-mapped) pointer — L2-coherent, L1 bypass,
+// because the data was written by other CTAs / other GPUs. Zero outside the image.
 __device__ __forceinline__ uint4 load_chunk(const pconv_geometry_t& g, const SourceSet& s,
                                             int64_t gr, int64_t gb) {
-    uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     if (gr < 0 || gr >= g.img_rows || gb + 16 <= 0 || gb >= g.img_cb) return z;
     const int orow = owner_of(gr, g.row_lo);
     const int64_t lrow = gr - g.row_lo[orow];
@@ -48,88 +66,22 @@ __device__ __forceinline__ uint4 load_chunk(const pconv_geometry_t& g, const Sou
                 return __ldcg(reinterpret_cast<const uint4*>(a));
         }
     }
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        const int64_t b = gb + t;
-        if (b < 0 || b >= g.img_cb) continue;
-        const int oc = owner_of(b, g.cb_lo);
-        const int d = orow * 3 + oc;
-        const uint8_t* base = s.p[d];
-        if (base == nullptr) continue;
-        const uint32_t v = __ldcg(base + lrow * s.pitch[d] + (b - g.cb_lo[oc]));
-        w[t >> 2] |= v << (8 * (t & 3));
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
+    return load_chunk_bytes(g, s, orow, lrow, gb);
 }
 
-// Load region rows [r0,r1) x chunk columns [c0,c1) (16-byte units) into buf (and mirror image-
-// exterior zero rows into buf_b so that both ping-pong buffers hold the zero padding).
-// Region (row i, byte x) <-> image (gr0 + i, gb0 + x).
-__device__ __forceinline__ void load_rect(uint8_t* __restrict__ buf, uint8_t* __restrict__ buf_b,
-                                          const pconv_geometry_t& g, const SourceSet& s,
-                                          int64_t gr0, int64_t gb0, int r0, int r1, int c0, int c1) {
-    const int ncols = c1 - c0;
-    const int total = (r1 - r0) * ncols;
-    uint4* b4 = reinterpret_cast<uint4*>(buf);
-    uint4* bb4 = reinterpret_cast<uint4*>(buf_b);
-    if (ncols == kChunksPerRow) {
-        // full-width: a warp reads one contiguous 512-byte row; 4 rows in flight per thread
-        const int cc = threadIdx.x & 31;
-        const int64_t gb = gb0 + 16 * cc;
-        for (int i = r0 + (threadIdx.x >> 5); i < r1; i += 4 * kWarps) {
-            uint4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int ii = i + u * kWarps;
-                v[u] = (ii < r1) ? load_chunk(g, s, gr0 + ii, gb) : make_uint4(0u, 0u, 0u, 0u);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int ii = i + u * kWarps;
-                if (ii < r1) {
-                    b4[ii * kChunksPerRow + cc] = v[u];
-                    const int64_t gr = gr0 + ii;
-                    if (bb4 != nullptr && (gr < 0 || gr >= g.img_rows))
-                        bb4[ii * kChunksPerRow + cc] = make_uint4(0u, 0u, 0u, 0u);
-                }
-            }
-        }
+// Store one 16-byte chunk at image position (gr, gb) into my tile, clipped to the tile.
+__device__ __forceinline__ void store_chunk(uint8_t* __restrict__ dst, const pconv_geometry_t& g,
+                                            int64_t gr, int64_t gb, const uint4& v) {
+    const int64_t lr = gr - g.row_lo[1], lb = gb - g.cb_lo[1];
+    const int64_t tile_rows = g.row_lo[2] - g.row_lo[1], tile_cb = g.cb_lo[2] - g.cb_lo[1];
+    if (lr < 0 || lr >= tile_rows || lb + 16 <= 0 || lb >= tile_cb) return;
+    uint8_t* a = dst + lr * g.pitch + lb;
+    if (lb >= 0 && lb + 16 <= tile_cb && (reinterpret_cast<uintptr_t>(a) & 15u) == 0) {
+        __stcg(reinterpret_cast<uint4*>(a), v);
     } else {
-        for (int idx = threadIdx.x; idx < total; idx += kThreads) {
-            const int i = r0 + idx / ncols, cc = c0 + idx % ncols;
-            const int64_t gr = gr0 + i;
-            b4[i * kChunksPerRow + cc] = load_chunk(g, s, gr, gb0 + 16 * cc);
-            if (bb4 != nullptr && (gr < 0 || gr >= g.img_rows))
-                bb4[i * kChunksPerRow + cc] = make_uint4(0u, 0u, 0u, 0u);
-        }
-    }
-}
-
-// Store region rows [r0,r1) x chunk columns [c0,c1) to my tile (clipped to the tile).
-__device__ __forceinline__ void store_rect(const uint8_t* __restrict__ buf, uint8_t* __restrict__ dst,
-                                           const pconv_geometry_t& g, int64_t gr0, int64_t gb0,
-                                           int r0, int r1, int c0, int c1) {
-    const int ncols = c1 - c0;
-    const int total = (r1 - r0) * ncols;
-    const uint4* b4 = reinterpret_cast<const uint4*>(buf);
-    const int64_t tile_rows = g.row_lo[2] - g.row_lo[1];
-    const int64_t tile_cb = g.cb_lo[2] - g.cb_lo[1];
-    for (int idx = threadIdx.x; idx < total; idx += kThreads) {
-        const int i = r0 + idx / ncols, cc = c0 + idx % ncols;
-        const int64_t lr = gr0 + i - g.row_lo[1];
-        const int64_t lb = gb0 + 16 * cc - g.cb_lo[1];
-        if (lr < 0 || lr >= tile_rows || lb + 16 <= 0 || lb >= tile_cb) continue;
-        const uint4 v = b4[i * kChunksPerRow + cc];
-        uint8_t* a = dst + lr * g.pitch + lb;
-        if (lb >= 0 && lb + 16 <= tile_cb && (reinterpret_cast<uintptr_t>(a) & 15u) == 0) {
-            __stcg(reinterpret_cast<uint4*>(a), v);
-        } else {
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int t = 0; t < 16; ++t)
-                if (lb + t >= 0 && lb + t < tile_cb) a[t] = (uint8_t)(w[t >> 2] >> (8 * (t & 3)));
-        }
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int t = 0; t < 16; ++t)
+            if (lb + t >= 0 && lb + t < tile_cb) a[t] = (uint8_t)(w[t >> 2] >> (8 * (t & 3)));
     }
 }
 

@@ -1,14 +1,14 @@
 // Device-side stencil core shared by the streaming and the resident kernels.
 //
-// Geometry (all kernels): a CTA of 512 threads (16 warps) owns a shared-memory *region* of RH rows
-// x 512 bytes (kSP). One warp spans the full region width: lane l owns the 16-byte strip
-// [16 l, 16 l + 16) of every row it works on, so the row loads/stores are conflict-free LDS.128 /
-// STS.128 and horizontal neighbours that fall outside a lane's strip come from the adjacent lane
-// with warp shuffles (never from shared memory). Warps split the rows of an iteration into 16
-// contiguous segments and *stream* down their segment: pushing input row r+1 completes output
-// row r. k iterations are fused per region (temporal blocking): iteration j recomputes
-// rows [j, RH-j) of the region, the outer ring goes stale by one pixel per iteration and the halo
-// (k rows, HB >= k*C bytes) absorbs it, so results are bit-identical to k global passes.
+// Geometry (all kernels): a CTA of 512 threads (16 warps) owns a *region* of RH = 16*R rows x 512
+// bytes (kSP) that lives in REGISTERS: warp w holds rows [w*R, (w+1)*R), lane l the 16-byte strip
+// [16 l, 16 l + 16) of each of them (R uint4 per thread). Horizontal neighbours that fall outside
+// a lane's strip come from the adjacent lane with warp shuffles; the row above / below a warp's
+// band comes from the adjacent warp through a 32 KB shared-memory edge buffer (2 rows per warp per
+// iteration) — the bulk of the data never touches shared memory between iterations. Rows are
+// *streamed*: pushing row r+1 completes output row r. k iterations are fused per region (temporal
+// blocking): the outer ring of the region goes stale by one pixel per iteration and the halo
+// (k rows, HB >= k*C bytes) absorbs it, so the interior is bit-identical to k global passes.
 //
 // An interleaved image is a byte stream whose horizontal neighbour is C bytes away (C = 1 grey,
 // 3 RGB): grey and RGB share every line of code below except the lane-shuffle patterns.
@@ -316,73 +316,91 @@ struct F32Path {
 };
 
 // ---------------------------------------------------------------------------------------------
-// One fused iteration over region rows [lo, hi) (1 <= lo, hi <= RH-1): s_src -> s_dst.
-// mask[j] clears output bytes that lie outside the image (zero padding must stay zero).
+// Band iteration. Warp w of a CTA owns region rows [w*R, (w+1)*R) and keeps them in REGISTERS
+// (rows[i] = this lane's 16-byte strip of band row i) for all fused iterations; only the row above
+// (`top`, last row of warp w-1) and the row below (`bottom`, first row of warp w+1) come from
+// shared memory. One call advances the whole band by one iteration in place: pushing row i+1
+// completes row i, whose raw value is no longer needed (the path state holds what is).
+// MASKED: rows/bytes outside the image are forced back to zero (zero padding must stay zero).
 // ---------------------------------------------------------------------------------------------
-template <int C>
-__device__ __forceinline__ void iterate_sep121(const uint8_t* __restrict__ s_src,
-                                               uint8_t* __restrict__ s_dst, int lo, int hi,
-                                               const uint4& mask, bool need_mask,
-                                               const FilterDev& f) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seg = (hi - lo + kWarps - 1) / kWarps;
-    const int a = lo + warp * seg;
-    const int b = min(a + seg, hi);
-    if (a >= b) return;  // warp-uniform
-    const uint4* src = reinterpret_cast<const uint4*>(s_src) + lane;
-    uint4* dst = reinterpret_cast<uint4*>(s_dst) + lane;
+template <bool MASKED>
+__device__ __forceinline__ uint4 apply_mask(uint4 o, const uint4& cmask, uint32_t rowmask, int i) {
+    if (MASKED) {
+        const bool v = (rowmask >> i) & 1u;
+        o.x = v ? (o.x & cmask.x) : 0u; o.y = v ? (o.y & cmask.y) : 0u;
+        o.z = v ? (o.z & cmask.z) : 0u; o.w = v ? (o.w & cmask.w) : 0u;
+    }
+    return o;
+}
+
+template <int C, int R, bool MASKED>
+__device__ __forceinline__ void band_sep121(uint4 (&rows)[R], const uint4& top, const uint4& bottom,
+                                            const uint4& cmask, uint32_t rowmask, const FilterDev& f) {
     Sep121Path<C> p(f);
-    p.prime0(src[(a - 1) * kChunksPerRow]);
-    p.prime1(src[a * kChunksPerRow]);
-    uint4 nxt = src[(a + 1) * kChunksPerRow];
-#pragma unroll 2
-    for (int r = a; r < b; ++r) {
-        const uint4 cur = nxt;
-        if (r + 1 < b) nxt = src[(r + 2) * kChunksPerRow];  // software prefetch (r+2 <= RH-1)
-        uint4 o = p.push(cur);
-        if (need_mask) { o.x &= mask.x; o.y &= mask.y; o.z &= mask.z; o.w &= mask.w; }
-        dst[r * kChunksPerRow] = o;
+    p.prime0(top);
+    p.prime1(rows[0]);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const uint4 o = p.push(i + 1 < R ? rows[i + 1] : bottom);
+        rows[i] = apply_mask<MASKED>(o, cmask, rowmask, i);
     }
 }
 
-template <template <int> class Path, int C>
-__device__ __forceinline__ void iterate_phased(const uint8_t* __restrict__ s_src,
-                                               uint8_t* __restrict__ s_dst, int lo, int hi,
-                                               const uint4& mask, bool need_mask,
-                                               const FilterDev& f) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int seg = (hi - lo + kWarps - 1) / kWarps;
-    const int a = lo + warp * seg;
-    const int b = min(a + seg, hi);
-    if (a >= b) return;
-    const uint4* src = reinterpret_cast<const uint4*>(s_src) + lane;
-    uint4* dst = reinterpret_cast<uint4*>(s_dst) + lane;
+template <template <int> class Path, int C, int R, bool MASKED, int I>
+struct PhasedSteps {
+    static __device__ __forceinline__ void run(Path<C>& p, uint4 (&rows)[R], const uint4& bottom,
+                                               const uint4& cmask, uint32_t rowmask) {
+        if constexpr (I < R) {
+            const uint4 nxt = (I + 1 < R) ? rows[(I + 1 < R) ? I + 1 : 0] : bottom;
+            const uint4 o = p.template push<I % 3>(nxt);
+            rows[I] = apply_mask<MASKED>(o, cmask, rowmask, I);
+            PhasedSteps<Path, C, R, MASKED, I + 1>::run(p, rows, bottom, cmask, rowmask);
+        }
+    }
+};
+
+template <template <int> class Path, int C, int R, bool MASKED>
+__device__ __forceinline__ void band_phased(uint4 (&rows)[R], const uint4& top, const uint4& bottom,
+                                            const uint4& cmask, uint32_t rowmask, const FilterDev& f) {
     Path<C> p(f);
     // priming rows behave like pushes with phases -2 and -1 (== 1 and 2 mod 3)
-    p.template prime0<1>(src[(a - 1) * kChunksPerRow]);
-    p.template prime1<2>(src[a * kChunksPerRow]);
-    auto emit = [&](int r, uint4 o) {
-        if (need_mask) { o.x &= mask.x; o.y &= mask.y; o.z &= mask.z; o.w &= mask.w; }
-        dst[r * kChunksPerRow] = o;
-    };
-    int r = a;
-    for (; r + 2 < b; r += 3) {  // phases rotate the accumulator roles without register moves
-        emit(r, p.template push<0>(src[(r + 1) * kChunksPerRow]));
-        emit(r + 1, p.template push<1>(src[(r + 2) * kChunksPerRow]));
-        emit(r + 2, p.template push<2>(src[(r + 3) * kChunksPerRow]));
-    }
-    if (r < b) emit(r, p.template push<0>(src[(r + 1) * kChunksPerRow]));
-    if (r + 1 < b) emit(r + 1, p.template push<1>(src[(r + 2) * kChunksPerRow]));
+    p.template prime0<1>(top);
+    p.template prime1<2>(rows[0]);
+    PhasedSteps<Path, C, R, MASKED, 0>::run(p, rows, bottom, cmask, rowmask);
 }
 
-template <int KIND, int C>
-__device__ __forceinline__ void iterate_region(const uint8_t* __restrict__ s_src,
-                                               uint8_t* __restrict__ s_dst, int lo, int hi,
-                                               const uint4& mask, bool need_mask,
+template <int KIND, int C, int R, bool MASKED>
+__device__ __forceinline__ void band_iterate(uint4 (&rows)[R], const uint4& top, const uint4& bottom,
+                                             const uint4& cmask, uint32_t rowmask, const FilterDev& f) {
+    if constexpr (KIND == PCONV_KIND_SEP121) band_sep121<C, R, MASKED>(rows, top, bottom, cmask, rowmask, f);
+    else if constexpr (KIND == PCONV_KIND_INT) band_phased<IntPath, C, R, MASKED>(rows, top, bottom, cmask, rowmask, f);
+    else band_phased<F32Path, C, R, MASKED>(rows, top, bottom, cmask, rowmask, f);
+}
+
+// Shared-memory exchange of band boundary rows between adjacent warps: edge[parity][warp][0|1][lane]
+struct EdgeBuffers {
+    uint4 row[2][kWarps][2][32];
+};
+
+// k fused iterations over a CTA region held in registers. One __syncthreads per iteration:
+// iteration `it` publishes into parity it&1 and everybody reads that parity after the barrier; the
+// next iteration publishes into the other parity, so a fast warp never overwrites rows a slow
+// warp is still reading.
+template <int KIND, int C, int R, bool MASKED>
+__device__ __forceinline__ void region_iterate(uint4 (&rows)[R], EdgeBuffers& eb, int k,
+                                               const uint4& cmask, uint32_t rowmask,
                                                const FilterDev& f) {
-    if (KIND == PCONV_KIND_SEP121) iterate_sep121<C>(s_src, s_dst, lo, hi, mask, need_mask, f);
-    else if (KIND == PCONV_KIND_INT) iterate_phased<IntPath, C>(s_src, s_dst, lo, hi, mask, need_mask, f);
-    else iterate_phased<F32Path, C>(s_src, s_dst, lo, hi, mask, need_mask, f);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int it = 0; it < k; ++it) {
+        const int par = it & 1;
+        eb.row[par][warp][0][lane] = rows[0];
+        eb.row[par][warp][1][lane] = rows[R - 1];
+        __syncthreads();
+        const uint4 top = warp > 0 ? eb.row[par][warp - 1][1][lane] : zero;
+        const uint4 bottom = warp < kWarps - 1 ? eb.row[par][warp + 1][0][lane] : zero;
+        band_iterate<KIND, C, R, MASKED>(rows, top, bottom, cmask, rowmask, f);
+    }
 }
 
 }  // namespace pconv

@@ -13,6 +13,9 @@
 // input region reaches into the neighbour, i.e. the ones that wait — interior CTAs never wait.
 // No NCCL, no host round trip between launches; the host enqueues all launches of a run at once.
 //
+// A CTA region (16*R rows x 512 B) is loaded from global memory straight into registers, iterated
+// k times there (stencil_core.cuh) and its interior stored straight back: shared memory only
+// carries two boundary rows per warp per iteration.
 // The persistent grid (one CTA per SM) walks the CTA regions of the tile round-robin.
 // Replaces, for the GPU path, the reference's launch-per-iteration thread-per-pixel kernels
 // (cuda/cuda_convolute.cu:66-87) and, for the multi-GPU path, its MPI iteration loop
@@ -39,15 +42,15 @@ struct StreamArgs {
     pconv_sync_t sync;
 };
 
-template <int KIND, int C>
+template <int KIND, int C, int R>
 __global__ void __launch_bounds__(kThreads, 1)
 stream_kernel(const __grid_constant__ StreamArgs A) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t s_wait_ns;
+    __shared__ EdgeBuffers eb;
+    __shared__ unsigned long long s_wait_ns;
     const pconv_geometry_t& g = A.g;
-    const int k = A.k, RH = A.TH + 2 * A.k;
-    uint8_t* buf0 = smem;
-    uint8_t* buf1 = smem + (size_t)RH * kSP;
+    constexpr int RH = kWarps * R;
+    const int k = A.k;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = A.ntx * A.nty;
     const int64_t tile_row_end = g.row_lo[2], tile_cb_end = g.cb_lo[2];
 
@@ -58,7 +61,7 @@ stream_kernel(const __grid_constant__ StreamArgs A) {
 
         // ---- halo protocol: wait for the neighbours this region reaches into --------------------
         if (A.sync.wait_value != 0u) {
-            if (threadIdx.x == 0) s_wait_ns = 0;
+            if (threadIdx.x == 0) s_wait_ns = 0ull;
             __syncthreads();
             if (threadIdx.x < 9 && threadIdx.x != 4) {
                 const int dy = (int)threadIdx.x / 3, dx = (int)threadIdx.x % 3;
@@ -69,36 +72,40 @@ stream_kernel(const __grid_constant__ StreamArgs A) {
                 if (rows_hit && cols_hit && A.src.p[threadIdx.x] != nullptr) {
                     const uint64_t ns = wait_flag(A.sync.local_flags + threadIdx.x, A.sync.wait_value,
                                                   A.sync.timeout_ns, A.sync.status);
-                    atomicMax(reinterpret_cast<unsigned long long*>(&s_wait_ns), (unsigned long long)ns);
+                    atomicMax(&s_wait_ns, (unsigned long long)ns);
                 }
             }
             __syncthreads();
             if (threadIdx.x == 0 && s_wait_ns) record_wait(A.sync.status, s_wait_ns);
         }
 
-        // ---- load region (+ zero rows outside the image in both buffers) ------------------------
-        load_rect(buf0, buf1, g, A.src, gr0, gb0, 0, RH, 0, kChunksPerRow);
-        bool need_mask;
-        const uint4 mask = column_mask(g, gb0, &need_mask);
-        // region rows that lie inside the image
-        const int img_lo = (int)max((int64_t)0, -gr0);
-        const int img_hi = (int)min((int64_t)RH, g.img_rows - gr0);
-        __syncthreads();
+        // ---- load my band: R independent 128-bit loads per thread, straight into registers ------
+        const int64_t grw = gr0 + (int64_t)warp * R;   // image row of my band row 0
+        const int64_t gb = gb0 + 16 * lane;            // image byte of my strip
+        uint4 rows[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) rows[i] = load_chunk(g, A.src, grw + i, gb);
 
-        // ---- k fused iterations, ping-pong in shared memory -------------------------------------
-        for (int it = 1; it <= k; ++it) {
-            const uint8_t* s_src = (it & 1) ? buf0 : buf1;
-            uint8_t* s_dst = (it & 1) ? buf1 : buf0;
-            const int lo = max(max(it, img_lo), 1);
-            const int hi = min(min(RH - it, img_hi), RH - 1);
-            if (lo < hi) iterate_region<KIND, C>(s_src, s_dst, lo, hi, mask, need_mask, A.f);
-            __syncthreads();
+        bool need_cols;
+        const uint4 cmask = column_mask(g, gb0, &need_cols);
+        uint32_t rowmask = 0;
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+            if (grw + i >= 0 && grw + i < g.img_rows) rowmask |= 1u << i;
+        const bool masked = need_cols || gr0 < 0 || gr0 + RH > g.img_rows;  // CTA-uniform
+
+        // ---- k fused iterations in registers ------------------------------------------------------
+        if (masked) region_iterate<KIND, C, R, true>(rows, eb, k, cmask, rowmask, A.f);
+        else region_iterate<KIND, C, R, false>(rows, eb, k, cmask, rowmask, A.f);
+
+        // ---- store the interior straight from registers ------------------------------------------
+        const bool col_in = (16 * lane >= A.HB) && (16 * lane < A.HB + A.TWB);
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            const int rr = warp * R + i;
+            if (col_in && rr >= k && rr < k + A.TH) store_chunk(A.dst, g, grw + i, gb, rows[i]);
         }
-
-        // ---- store the interior ------------------------------------------------------------------
-        const uint8_t* fin = (k & 1) ? buf1 : buf0;
-        store_rect(fin, A.dst, g, gr0, gb0, k, k + A.TH, A.HB / 16, (A.HB + A.TWB) / 16);
-        __syncthreads();
+        __syncthreads();  // edge buffers are reused by the next tile
     }
 
     // ---- halo protocol: publish "launch done" to the neighbours -----------------------------------
@@ -127,17 +134,31 @@ stream_kernel(const __grid_constant__ StreamArgs A) {
 
 using KernelFn = void (*)(const StreamArgs);
 
-template <int KIND, int C>
-static KernelFn get_kernel() { return stream_kernel<KIND, C>; }
+// Band heights compiled in. Larger R = taller region = less halo recompute; smaller R = more CTAs
+// for small tiles (strong scaling). F32 keeps 48 accumulator registers, so its bands are shorter.
+// (register budget: 128/thread at 512 threads; the lists below are what fits without spilling)
+#define PCONV_FOR_R_SEP(X) X(2) X(4) X(7) X(10) X(14)
+#define PCONV_FOR_R_INT(X) X(2) X(4) X(7) X(10)
+#define PCONV_FOR_R_F32(X) X(2) X(4) X(6) X(8) X(10)
 
-static KernelFn pick_kernel(int kind, int C) {
+template <int KIND, int C>
+static KernelFn pick_r(int R) {
+#define CASE(RR) if (R == RR) return stream_kernel<KIND, C, RR>;
+    if constexpr (KIND == PCONV_KIND_F32) { PCONV_FOR_R_F32(CASE) }
+    else if constexpr (KIND == PCONV_KIND_INT) { PCONV_FOR_R_INT(CASE) }
+    else { PCONV_FOR_R_SEP(CASE) }
+#undef CASE
+    return nullptr;
+}
+
+static KernelFn pick_kernel(int kind, int C, int R) {
     switch (kind * 8 + C) {
-        case PCONV_KIND_SEP121 * 8 + 1: return get_kernel<PCONV_KIND_SEP121, 1>();
-        case PCONV_KIND_SEP121 * 8 + 3: return get_kernel<PCONV_KIND_SEP121, 3>();
-        case PCONV_KIND_INT * 8 + 1: return get_kernel<PCONV_KIND_INT, 1>();
-        case PCONV_KIND_INT * 8 + 3: return get_kernel<PCONV_KIND_INT, 3>();
-        case PCONV_KIND_F32 * 8 + 1: return get_kernel<PCONV_KIND_F32, 1>();
-        case PCONV_KIND_F32 * 8 + 3: return get_kernel<PCONV_KIND_F32, 3>();
+        case PCONV_KIND_SEP121 * 8 + 1: return pick_r<PCONV_KIND_SEP121, 1>(R);
+        case PCONV_KIND_SEP121 * 8 + 3: return pick_r<PCONV_KIND_SEP121, 3>(R);
+        case PCONV_KIND_INT * 8 + 1: return pick_r<PCONV_KIND_INT, 1>(R);
+        case PCONV_KIND_INT * 8 + 3: return pick_r<PCONV_KIND_INT, 3>(R);
+        case PCONV_KIND_F32 * 8 + 1: return pick_r<PCONV_KIND_F32, 1>(R);
+        case PCONV_KIND_F32 * 8 + 3: return pick_r<PCONV_KIND_F32, 3>(R);
         default: return nullptr;
     }
 }
@@ -146,18 +167,23 @@ static KernelFn pick_kernel(int kind, int C) {
 
 using namespace pconv;
 
-extern "C" int pconv_stream_max_region_rows(int ctas_per_sm) {
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    const int budget = (pconv_rt::max_optin_smem() - 1024) / ctas_per_sm - 1024;
-    return budget / (2 * kSP);
+// Band heights available for a filter kind (rows per warp; region rows = 16 * R).
+extern "C" int pconv_stream_band_heights(int kind, int* out, int cap) {
+    int n = 0;
+#define PUSH(RR) { if (n < cap) out[n] = RR; ++n; }
+    if (kind == PCONV_KIND_F32) { PCONV_FOR_R_F32(PUSH) }
+    else if (kind == PCONV_KIND_INT) { PCONV_FOR_R_INT(PUSH) }
+    else { PCONV_FOR_R_SEP(PUSH) }
+#undef PUSH
+    return n;
 }
 
 extern "C" int pconv_stream_launch(const pconv_stream_params_t* p, void* stream) {
     if (!p) return pconv_rt::fail("null params");
     const pconv_geometry_t& g = p->g;
     if (p->k < 1 || p->TH < 1 || p->TWB < 16 || (p->TWB & 15) || (p->HB & 15) ||
-        p->HB < p->k * g.C || p->TWB + 2 * p->HB > kSP)
-        return pconv_rt::fail("bad region geometry (k/TH/TWB/HB)");
+        p->HB < p->k * g.C || p->TWB + 2 * p->HB > kSP || p->TH + 2 * p->k > kWarps * p->R)
+        return pconv_rt::fail("bad region geometry (k/TH/TWB/HB/R)");
     const int64_t tile_rows = g.row_lo[2] - g.row_lo[1], tile_cb = g.cb_lo[2] - g.cb_lo[1];
     if (tile_rows <= 0 || tile_cb <= 0) return pconv_rt::fail("empty tile");
     // the halo may only reach into the *adjacent* tiles
@@ -166,8 +192,8 @@ extern "C" int pconv_stream_launch(const pconv_stream_params_t* p, void* stream)
         if ((nr > 0 && nr < p->k) || (nc > 0 && nc < (int64_t)p->k * g.C))
             return pconv_rt::fail("halo depth exceeds a neighbouring tile");
     }
-    KernelFn fn = pick_kernel(p->filt.kind, g.C);
-    if (!fn) return pconv_rt::fail("unsupported (filter kind, channels) combination");
+    KernelFn fn = pick_kernel(p->filt.kind, g.C, p->R);
+    if (!fn) return pconv_rt::fail("unsupported (filter kind, channels, band height) combination");
 
     StreamArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -184,18 +210,11 @@ extern "C" int pconv_stream_launch(const pconv_stream_params_t* p, void* stream)
     a.sync = p->sync;
     if (a.sync.timeout_ns == 0) a.sync.timeout_ns = 10ull * 1000 * 1000 * 1000;
 
-    const int RH = p->TH + 2 * p->k;
-    const size_t smem = (size_t)2 * RH * kSP;
-    if ((int)smem > pconv_rt::max_optin_smem() - 1024) return pconv_rt::fail("region does not fit in shared memory");
-    cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "cudaFuncSetAttribute");
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, kThreads, smem);
-    if (e != cudaSuccess || occ < 1) return pconv_rt::fail_cuda(e, "occupancy");
     const int ntiles = a.ntx * a.nty;
-    int grid = p->grid > 0 ? p->grid : pconv_rt::sm_count() * occ;
+    int grid = p->grid > 0 ? p->grid : pconv_rt::sm_count();
     if (grid > ntiles) grid = ntiles;
-    fn<<<grid, kThreads, smem, (cudaStream_t)stream>>>(a);
+    fn<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e;
     pconv_rt::count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "stream_kernel launch");

@@ -34,7 +34,7 @@ class Sync(C.Structure):
 class StreamParams(C.Structure):
     _fields_ = [("g", Geometry), ("src", C.c_void_p * 9), ("src_pitch", C.c_int64 * 9),
                 ("dst", C.c_void_p), ("filt", FilterSpec), ("k", C.c_int32), ("TH", C.c_int32),
-                ("TWB", C.c_int32), ("HB", C.c_int32), ("grid", C.c_int32), ("pad_", C.c_int32),
+                ("TWB", C.c_int32), ("HB", C.c_int32), ("grid", C.c_int32), ("R", C.c_int32),
                 ("sync", Sync)]
 
 
@@ -58,7 +58,7 @@ def lib() -> C.CDLL:
     L = C.CDLL(os.fspath(path))
     vp, i64 = C.c_void_p, C.c_int64
     L.pconv_stream_launch.argtypes = [C.POINTER(StreamParams), vp]
-    L.pconv_stream_max_region_rows.argtypes = [C.c_int]
+    L.pconv_stream_band_heights.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int]
     if hasattr(L, "pconv_resident_launch"):
         L.pconv_resident_launch.argtypes = [C.POINTER(ResidentParams), vp]
     L.pconv_cuda_set_device.argtypes = [C.c_int]
@@ -127,8 +127,11 @@ def launch_count() -> int:
     return int(lib().pconv_cuda_launch_count())
 
 
-def max_region_rows(ctas_per_sm: int = 1) -> int:
-    return int(lib().pconv_stream_max_region_rows(ctas_per_sm))
+def band_heights(kind: int) -> list[int]:
+    """Band heights R (rows per warp; region = 16*R rows) compiled for a filter kind."""
+    buf = (C.c_int * 16)()
+    n = int(lib().pconv_stream_band_heights(kind, buf, 16))
+    return [int(buf[i]) for i in range(n)]
 
 
 def malloc(nbytes: int) -> int:

@@ -117,7 +117,7 @@ class TileDriver:
             p.sync.remote_flags[d] = (nb.flags + 4 * (8 - d)) if (nb is not None and d != 4) else None
         p.dst = self.mem.bufs[src_parity ^ 1]
         p.filt = self.filt.spec
-        p.k, p.TH, p.TWB, p.HB, p.grid = k, plan.TH, plan.TWB, plan.HB, grid_ctas
+        p.k, p.TH, p.TWB, p.HB, p.grid, p.R = k, plan.TH, plan.TWB, plan.HB, grid_ctas, plan.R
         # (a shallower tail launch, k < plan.k, keeps TH/HB: HB >= k*C still holds and RH shrinks)
         p.sync.local_flags = self.mem.flags
         p.sync.done_counter = self.mem.counter
@@ -173,20 +173,21 @@ class TileDriver:
 
 
 def make_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int | None = None,
-              sms: int | None = None, max_rh: int | None = None) -> StreamPlan:
+              sms: int | None = None, bands: list[int] | None = None,
+              band: int | None = None) -> StreamPlan:
     """The (rank-independent) stream plan for a grid."""
     Cn = grid.channels
     multi_r, multi_c = grid.grid_rows > 1, grid.grid_cols > 1
     kw = {}
     if sms:
         kw["sms"] = sms
-    if max_rh:
-        kw["max_rh"] = max_rh
+    if bands:
+        kw["bands"] = bands
     return plan_stream(grid.max_tile_rows(), grid.max_tile_cols() * Cn, Cn, filt.kind,
                        max(loops, 1),
                        min_nbr_rows=grid.min_tile_rows() if multi_r else None,
                        min_nbr_cols=grid.min_tile_cols() if multi_c else None,
-                       force_k=halo_depth, **kw)
+                       force_k=halo_depth, force_R=band, **kw)
 
 
 class VirtualCluster:
@@ -208,7 +209,7 @@ class VirtualCluster:
             nbrs = [self.mems[n] if n >= 0 else None for n in grid.neighbors(r)]
             self.drivers.append(TileDriver(grid, r, filt, self.mems[r], nbrs, self.pitch, stream))
         self.sms = K.sm_count()
-        self.max_rh = K.max_region_rows(1)
+        self.bands = K.band_heights(filt.kind)
         self.parity = 0
         self.last = RunStats()
 
@@ -245,7 +246,7 @@ class VirtualCluster:
         if loops <= 0:
             self.last = stats
             return stats
-        plan = plan or make_plan(self.grid, self.filt, loops, self.halo_depth, self.sms, self.max_rh)
+        plan = plan or make_plan(self.grid, self.filt, loops, self.halo_depth, self.sms, self.bands)
         stats.plan = plan
         multi = self.use_flags and self.grid.workers > 1
         for d in self.drivers:

@@ -21,13 +21,14 @@ def main():
     ap.add_argument("--filter", default="gaussian")
     ap.add_argument("--workers", type=int, default=1)
     ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--band", type=int, default=0)
     ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
     f = Filter.parse(a.filter)
     g = TileGrid.create(a.height, a.width, a.channels, a.workers)
     vc = VirtualCluster(g, f, halo_depth=a.k or None)
     vc.synth(1)
-    plan = make_plan(g, f, a.loops, a.k or None, vc.sms, vc.max_rh)
+    plan = make_plan(g, f, a.loops, a.k or None, vc.sms, vc.bands, a.band or None)
     vc.run(a.loops, plan)
     K.device_sync()
     best = 1e9
