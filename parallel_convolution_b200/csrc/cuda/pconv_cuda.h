@@ -59,6 +59,16 @@ typedef struct pconv_stream_params {
 } pconv_stream_params_t;
 
 int pconv_stream_launch(const pconv_stream_params_t* p, void* stream);
+// Enqueue a whole run from native code (one call instead of one Python round trip per launch):
+// `pp` holds 2*nranks parameter blocks, [2*r + 0] reading buffer parity A and [2*r + 1] parity B of
+// (virtual) rank r; launch i uses block (i & 1) with k = ks[i]; with use_flags the epochs are
+// signal = epoch0 + i + 1 and wait = (i ? epoch0 + i : first_wait).
+int pconv_stream_run(const pconv_stream_params_t* pp, int nranks, const int32_t* ks, int nlaunch,
+                     uint32_t epoch0, int use_flags, uint32_t first_wait, void* stream);
+// Stand-alone halo-protocol step (1 CTA): wait until every existing neighbour reached wait_value,
+// then announce signal_value to them. Brackets host/device copies into a tile buffer between runs
+// so that back-to-back steps need no host barrier (bench.py, streaming ingest).
+int pconv_sync_launch(const pconv_sync_t* s, void* stream);
 // Band heights compiled for a filter kind; returns the count, fills out[0..cap).
 int pconv_stream_band_heights(int kind, int* out, int cap);
 

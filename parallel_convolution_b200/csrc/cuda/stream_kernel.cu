@@ -132,6 +132,20 @@ stream_kernel(const __grid_constant__ StreamArgs A) {
     }
 }
 
+__global__ void sync_kernel(const pconv_sync_t S) {
+    if (S.wait_value != 0u && threadIdx.x < 9 && threadIdx.x != 4 && S.remote_flags[threadIdx.x] != nullptr) {
+        const uint64_t ns = wait_flag(S.local_flags + threadIdx.x, S.wait_value, S.timeout_ns, S.status);
+        if (ns) record_wait(S.status, ns);
+    }
+    __syncthreads();
+    if (S.signal_value != 0u && threadIdx.x == 0 && !S.inject_drop_signal) {
+        __threadfence_system();
+#pragma unroll
+        for (int d = 0; d < 9; ++d)
+            if (d != 4 && S.remote_flags[d] != nullptr) st_release_sys(S.remote_flags[d], S.signal_value);
+    }
+}
+
 using KernelFn = void (*)(const StreamArgs);
 
 // Band heights compiled in. Larger R = taller region = less halo recompute; smaller R = more CTAs
@@ -218,5 +232,37 @@ extern "C" int pconv_stream_launch(const pconv_stream_params_t* p, void* stream)
     pconv_rt::count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "stream_kernel launch");
+    return 0;
+}
+
+extern "C" int pconv_stream_run(const pconv_stream_params_t* pp, int nranks, const int32_t* ks,
+                                int nlaunch, uint32_t epoch0, int use_flags, uint32_t first_wait,
+                                void* stream) {
+    if (!pp || !ks || nranks < 1 || nlaunch < 0) return pconv_rt::fail("bad run arguments");
+    for (int i = 0; i < nlaunch; ++i) {
+        for (int r = 0; r < nranks; ++r) {
+            pconv_stream_params_t p = pp[2 * r + (i & 1)];
+            p.k = ks[i];
+            if (use_flags) {
+                p.sync.signal_value = epoch0 + (uint32_t)i + 1u;
+                p.sync.wait_value = i ? epoch0 + (uint32_t)i : first_wait;
+            } else {
+                p.sync.signal_value = p.sync.wait_value = 0u;
+            }
+            const int rc = pconv_stream_launch(&p, stream);
+            if (rc != 0) return rc;
+        }
+    }
+    return 0;
+}
+
+extern "C" int pconv_sync_launch(const pconv_sync_t* s, void* stream) {
+    if (!s) return pconv_rt::fail("null sync");
+    pconv_sync_t a = *s;
+    if (a.timeout_ns == 0) a.timeout_ns = 10ull * 1000 * 1000 * 1000;
+    sync_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+    pconv_rt::count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "sync_kernel launch");
     return 0;
 }

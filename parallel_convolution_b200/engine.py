@@ -1,0 +1,347 @@
+"""ConvEngine — the public API: iterate a 3x3 filter over a raw image on 1..N workers.
+
+One engine instance == one rank. Process model:
+
+* **single process** (no ``torch.distributed``): ``backend="fused"`` runs on one GPU; with
+  ``workers=N`` the image is decomposed into N *virtual ranks* on that GPU (same kernels, flags and
+  owner lookup as the multi-GPU path). ``backend="cpu"`` runs the native CPU engine.
+* **one process per GPU** (``torchrun``; ``torch.distributed`` initialised, backend nccl or gloo):
+  rank r owns tile r of the grid. ``fused`` pulls halos through NVLink peer memory inside the
+  kernel; ``nccl`` is the send/recv baseline; ``cpu`` is the MPI-like host backend over gloo.
+
+Typical use (the call a user makes; ``bench.py`` times exactly this)::
+
+    eng = ConvEngine(width=1920, height=2520, channels=3, filter="gaussian")
+    out = eng.run(image, loops=100)          # numpy uint8 in, numpy uint8 out (rank 0)
+
+Replaces the reference's three ``main`` programs (``mpi/mpi_conv.c:18-297``,
+``mpi_omp/mpi_omp_conv.c``, ``cuda/main.c:10-55`` + ``gpuConvolute``).
+"""
+from __future__ import annotations
+
+import os
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .models.filters import Filter
+from .ops import host as H
+from .parallel.decomposition import TileGrid
+
+
+@dataclass
+class EngineConfig:
+    width: int
+    height: int
+    channels: int = 1
+    filter: str | Filter = "gaussian"
+    backend: str = "auto"            # auto | fused | nccl | cpu
+    workers: int | None = None       # single-process: number of virtual ranks (default 1)
+    grid: tuple[int, int] | None = None
+    halo_depth: int | None = None    # temporal-blocking depth k (None: planner decides)
+    mode: str = "auto"               # fused backend: auto | stream | resident
+    threads: int = 0                 # cpu backend: OpenMP threads per rank
+    device: int | None = None        # CUDA device index (default: LOCAL_RANK or 0)
+    timeout_ms: float = 10_000.0     # in-kernel watchdog for neighbour flags
+
+
+@dataclass
+class RunReport:
+    loops: int = 0
+    elapsed_ms: float = 0.0          # device-timed (fused/nccl) or host-timed (cpu), max over ranks
+    launches: int = 0
+    backend: str = ""
+    plan: dict = field(default_factory=dict)
+    max_wait_us: float = 0.0         # exposed halo wait: longest single spin of any CTA
+    sum_wait_us: float = 0.0
+    waits: int = 0
+    watchdog: bool = False
+
+    def mpixels_per_s(self, width: int, height: int) -> float:
+        return width * height * self.loops / max(self.elapsed_ms, 1e-9) / 1e3
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist
+    except Exception:
+        pass
+    return None
+
+
+class ConvEngine:
+    def __init__(self, width: int | None = None, height: int | None = None, channels: int = 1,
+                 filter: str | Filter = "gaussian", config: EngineConfig | None = None, **kw):
+        cfg = config or EngineConfig(width=width, height=height, channels=channels, filter=filter, **kw)
+        self.cfg = cfg
+        self.filter = cfg.filter if isinstance(cfg.filter, Filter) else Filter.parse(str(cfg.filter))
+        self.dist = _dist()
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.distributed = self.world > 1
+        self.backend = self._pick_backend(cfg.backend)
+        workers = self.world if self.distributed else (cfg.workers or 1)
+        if self.backend == "cpu" and not self.distributed:
+            workers = 1
+        self.grid = TileGrid.create(cfg.height, cfg.width, cfg.channels, workers, cfg.grid)
+        self.report = RunReport(backend=self.backend)
+        self._impl = None
+        self._setup()
+
+    # ------------------------------------------------------------------------------------------
+    def _pick_backend(self, want: str) -> str:
+        want = {"host": "cpu", "gpu": "fused", "cuda": "fused"}.get(want, want)
+        if want not in ("auto", "fused", "nccl", "cpu"):
+            raise ValueError(f"unknown backend {want!r}")
+        if want == "auto":
+            from .ops import cuda as K
+            return "fused" if K.available() else "cpu"
+        if want in ("fused", "nccl"):
+            from .ops import cuda as K
+            if not K.available():
+                raise RuntimeError(f"backend {want!r} needs a CUDA device and libpconv_cuda.so")
+        return want
+
+    def _setup(self) -> None:
+        cfg = self.cfg
+        if self.backend == "cpu":
+            from .parallel.host_backend import HostTile
+            k = cfg.halo_depth or 1
+            self._impl = HostTile(self.grid, self.rank if self.distributed else 0, self.filter, k,
+                                  cfg.threads, self.dist if self.distributed else None)
+            return
+        from .ops import cuda as K
+        dev = cfg.device if cfg.device is not None else int(os.environ.get("LOCAL_RANK", "0"))
+        if dev >= K.device_count():
+            dev = dev % max(K.device_count(), 1)
+        K.set_device(dev)
+        self.device = dev
+        if self.backend == "fused":
+            from .parallel.fused_runtime import FusedRuntime
+            self._impl = FusedRuntime(self.grid, self.filter, self.rank, self.world, self.dist,
+                                      halo_depth=cfg.halo_depth, mode=cfg.mode,
+                                      timeout_ms=cfg.timeout_ms)
+        else:
+            from .parallel.nccl_backend import NcclRuntime
+            self._impl = NcclRuntime(self.grid, self.filter, self.rank, self.world, self.dist,
+                                     halo_depth=cfg.halo_depth)
+
+    def close(self) -> None:
+        if self._impl is not None and hasattr(self._impl, "close"):
+            self._impl.close()
+        self._impl = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- tiles this process owns -------------------------------------------------------------------
+    @property
+    def local_tiles(self):
+        if self.distributed:
+            return [self.grid.tile(self.rank)]
+        return self.grid.tiles()
+
+    def _slice(self, img2d: np.ndarray, t) -> np.ndarray:
+        C = self.grid.channels
+        return img2d[t.row0:t.row0 + t.rows, t.col0 * C:(t.col0 + t.cols) * C]
+
+    # -- data in -------------------------------------------------------------------------------------
+    def load_image(self, image: np.ndarray) -> None:
+        """Every rank passes the full image (or at least its own tile region is read from it)."""
+        g = self.grid
+        img = np.asarray(image, dtype=np.uint8).reshape(g.height, g.row_bytes)
+        if self.backend == "cpu":
+            self._impl.load(self._slice(img, self._impl.tile))
+        else:
+            self._impl.upload({t.rank: self._slice(img, t) for t in self.local_tiles})
+
+    def load_file(self, path: str) -> None:
+        """Rank-parallel read: every rank reads exactly its tile rows (64-bit offsets)."""
+        g, C = self.grid, self.grid.channels
+        need = g.height * g.row_bytes
+        have = H.file_size(path)
+        if have < need:
+            raise ValueError(f"{path}: {have} bytes, need {need} for {g.width}x{g.height}x{C}")
+        tiles = {t.rank: H.read_rect(path, g.row_bytes, t.row0, t.rows, t.col0 * C, t.cols * C)
+                 for t in self.local_tiles}
+        if self.backend == "cpu":
+            self._impl.load(tiles[self._impl.tile.rank])
+        else:
+            self._impl.upload(tiles)
+
+    def load_synthetic(self, seed: int = 1) -> None:
+        """Deterministic random image, generated per tile (on the device for GPU backends)."""
+        g, C = self.grid, self.grid.channels
+        if self.backend == "cpu":
+            t = self._impl.tile
+            self._impl.load(H.synth_rect(seed, g.row_bytes, t.row0, t.rows, t.col0 * C, t.cols * C))
+        else:
+            self._impl.synth(seed)
+
+    # -- compute -------------------------------------------------------------------------------------
+    def iterate(self, loops: int, sync: bool = True) -> RunReport:
+        """Apply the filter ``loops`` times to the loaded tiles. Device-timed for GPU backends."""
+        rep = RunReport(loops=loops, backend=self.backend)
+        if self.backend == "cpu":
+            if self.distributed:
+                self.dist.barrier()
+            t0 = time.perf_counter()
+            self._impl.iterate(loops)
+            ms = (time.perf_counter() - t0) * 1e3
+            rep.elapsed_ms = self._max_over_ranks(ms)
+            rep.launches = 0
+            rep.plan = {"k": self._impl.k, "exchanges": self._impl.exchanges}
+        else:
+            self._impl.run(loops, rep, sync=sync)
+            if sync:
+                rep.elapsed_ms = self._max_over_ranks(rep.elapsed_ms)
+        self.report = rep
+        return rep
+
+    def _max_over_ranks(self, v: float) -> float:
+        if not self.distributed:
+            return v
+        import torch
+        dev = "cpu" if self.dist.get_backend() == "gloo" else f"cuda:{self.device}"
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # -- data out ------------------------------------------------------------------------------------
+    def local_results(self) -> dict[int, np.ndarray]:
+        if self.backend == "cpu":
+            return {self._impl.tile.rank: self._impl.result()}
+        return self._impl.download()
+
+    def gather(self) -> np.ndarray | None:
+        """Full result image on rank 0 (None elsewhere)."""
+        g, C = self.grid, self.grid.channels
+        local = self.local_results()
+        if not self.distributed:
+            out = np.empty((g.height, g.row_bytes), dtype=np.uint8)
+            for r, tile in local.items():
+                self._slice(out, g.tile(r))[:] = tile
+            return self._shape(out)
+        table = [None] * self.world if self.rank == 0 else None
+        self.dist.gather_object(local[self.rank], table, dst=0)
+        if self.rank != 0:
+            return None
+        out = np.empty((g.height, g.row_bytes), dtype=np.uint8)
+        for r, tile in enumerate(table):
+            self._slice(out, g.tile(r))[:] = tile
+        return self._shape(out)
+
+    def _shape(self, out2d: np.ndarray) -> np.ndarray:
+        g = self.grid
+        return out2d.reshape(g.height, g.width) if g.channels == 1 else out2d.reshape(g.height, g.width, g.channels)
+
+    def save_file(self, path: str) -> None:
+        """Rank-parallel write (rank 0 creates/truncates, then every rank writes its tile)."""
+        g, C = self.grid, self.grid.channels
+        if self.rank == 0:
+            H.create_file(path, g.height * g.row_bytes)
+        if self.distributed:
+            self.dist.barrier()
+        for r, tile in self.local_results().items():
+            t = g.tile(r)
+            H.write_rect(path, g.row_bytes, t.row0, t.col0 * C, np.ascontiguousarray(tile))
+        if self.distributed:
+            self.dist.barrier()
+
+    # -- streaming steps (GPU backends): asynchronous, no host barrier between steps -------------------
+    def make_input_pool(self, count: int, seed: int = 1) -> int:
+        """Device-resident pool of ``count`` synthetic input images (per local tile)."""
+        from .ops import cuda as K
+        rt = self._impl
+        self._pool = []
+        for i in range(count):
+            bufs = {}
+            for r in rt.local_ranks:
+                t, C = self.grid.tile(r), self.grid.channels
+                p = K.malloc(rt.mems[r].nbytes)
+                K.synth_rect(seed + i, self.grid.row_bytes, t.row0, t.rows, t.col0 * C, t.cols * C,
+                             p, rt.pitch, rt.stream)
+                bufs[r] = p
+            self._pool.append(bufs)
+        K.stream_sync(rt.stream)
+        return count
+
+    def enqueue_step_from_pool(self, index: int, loops: int) -> int:
+        """Enqueue one step: pool image -> tile buffers (device copy) -> ``loops`` iterations.
+        Returns the number of kernels launched. Ordering against neighbours is in-stream."""
+        from .ops import cuda as K
+        rt = self._impl
+        n = rt.begin_input()
+        for r in rt.local_ranks:
+            K.memcpy_async(rt.mems[r].bufs[0], self._pool[index % len(self._pool)][r],
+                           rt.mems[r].nbytes - 256, K.D2D, rt.stream)
+        rt.parity = 0
+        n += rt.end_input()
+        _, launches = rt.enqueue(loops)
+        return n + launches
+
+    def pinned_buffers(self) -> tuple[dict, dict]:
+        """Pinned host staging (input, output) per local tile, dense rows x tile_bytes."""
+        from .ops import cuda as K
+        import ctypes
+        ins, outs = {}, {}
+        for r in self._impl.local_ranks:
+            t, C = self.grid.tile(r), self.grid.channels
+            n = t.rows * t.cols * C
+            for table in (ins, outs):
+                p = K.host_alloc(n)
+                arr = np.ctypeslib.as_array((ctypes.c_uint8 * n).from_address(p)).reshape(t.rows, t.cols * C)
+                table[r] = arr
+        return ins, outs
+
+    def enqueue_step_pinned(self, host_in: dict, host_out: dict, loops: int) -> int:
+        """Enqueue one end-to-end step: H2D of the input tiles (pinned), ``loops`` iterations, D2H of
+        the result tiles (pinned). Asynchronous; ``synchronize()`` completes it."""
+        from .ops import cuda as K
+        rt = self._impl
+        n = rt.begin_input()
+        for r in rt.local_ranks:
+            a = host_in[r]
+            K.memcpy2d_async(rt.mems[r].bufs[0], rt.pitch, a.ctypes.data, a.shape[1], a.shape[1],
+                             a.shape[0], K.H2D, rt.stream)
+        rt.parity = 0
+        n += rt.end_input()
+        _, launches = rt.enqueue(loops)
+        for r in rt.local_ranks:
+            o = host_out[r]
+            K.memcpy2d_async(o.ctypes.data, o.shape[1], rt.mems[r].bufs[rt.parity], rt.pitch,
+                             o.shape[1], o.shape[0], K.D2H, rt.stream)
+        return n + launches
+
+    def synchronize(self) -> None:
+        from .ops import cuda as K
+        K.stream_sync(self._impl.stream)
+
+    @property
+    def stream(self) -> int:
+        return self._impl.stream
+
+    # -- one-call conveniences -----------------------------------------------------------------------
+    def run(self, image: np.ndarray, loops: int) -> np.ndarray | None:
+        self.load_image(image)
+        self.iterate(loops)
+        return self.gather()
+
+    def run_file(self, path_in: str, loops: int, path_out: str | None = None) -> RunReport:
+        """``prog image width height loops {rgb|grey}``: read, iterate, write ``blur_<image>``.
+
+        The output name prefixes the *basename* (the reference prefixes the whole path, defect D8).
+        """
+        if path_out is None:
+            d, b = os.path.split(path_in)
+            path_out = os.path.join(d, "blur_" + b)
+        self.load_file(path_in)
+        rep = self.iterate(loops)
+        self.save_file(path_out)
+        return rep

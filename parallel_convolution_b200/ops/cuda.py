@@ -58,6 +58,9 @@ def lib() -> C.CDLL:
     L = C.CDLL(os.fspath(path))
     vp, i64 = C.c_void_p, C.c_int64
     L.pconv_stream_launch.argtypes = [C.POINTER(StreamParams), vp]
+    L.pconv_stream_run.argtypes = [C.POINTER(StreamParams), C.c_int, C.POINTER(C.c_int32), C.c_int,
+                                   C.c_uint32, C.c_int, C.c_uint32, vp]
+    L.pconv_sync_launch.argtypes = [C.POINTER(Sync), vp]
     L.pconv_stream_band_heights.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int]
     if hasattr(L, "pconv_resident_launch"):
         L.pconv_resident_launch.argtypes = [C.POINTER(ResidentParams), vp]
@@ -264,6 +267,18 @@ def unpack_rect(tile: int, pitch: int, row0: int, byte0: int, rows: int, nbytes:
 
 def stream_launch(p: StreamParams, stream: int) -> None:
     _check(lib().pconv_stream_launch(C.byref(p), stream), "stream_launch")
+
+
+def stream_run(blocks, nranks: int, ks: list[int], epoch0: int, use_flags: bool, stream: int,
+               first_wait: int = 0) -> None:
+    """``blocks``: ctypes array of 2*nranks StreamParams (see pconv_stream_run)."""
+    arr = (C.c_int32 * len(ks))(*ks)
+    _check(lib().pconv_stream_run(blocks, nranks, arr, len(ks), epoch0, 1 if use_flags else 0,
+                                  first_wait, stream), "stream_run")
+
+
+def sync_launch(s: Sync, stream: int) -> None:
+    _check(lib().pconv_sync_launch(C.byref(s), stream), "sync_launch")
 
 
 def resident_launch(p: ResidentParams, stream: int) -> None:

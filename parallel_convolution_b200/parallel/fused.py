@@ -191,77 +191,51 @@ def make_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int | None =
 
 
 class VirtualCluster:
-    """N tiles on one device in one process; launches are interleaved rank by rank on one stream.
+    """N tiles on one device in one process (``FusedRuntime`` with ``world == 1``).
 
     The kernels, flag protocol and owner lookup are exactly the multi-GPU ones; only the pointers
     are local. Used by the tests and by ``ConvEngine(workers=N)`` on a single GPU.
     """
 
-    def __init__(self, grid: TileGrid, filt: Filter, stream: int = 0,
-                 halo_depth: int | None = None, use_flags: bool = True):
-        self.grid, self.filt, self.stream = grid, filt, stream
-        self.halo_depth, self.use_flags = halo_depth, use_flags
-        self.pitch = tile_pitch(grid)
-        rows = grid.max_tile_rows()
-        self.mems = [RankMemory.allocate(rows, self.pitch) for _ in range(grid.workers)]
-        self.drivers: list[TileDriver] = []
-        for r in range(grid.workers):
-            nbrs = [self.mems[n] if n >= 0 else None for n in grid.neighbors(r)]
-            self.drivers.append(TileDriver(grid, r, filt, self.mems[r], nbrs, self.pitch, stream))
-        self.sms = K.sm_count()
-        self.bands = K.band_heights(filt.kind)
-        self.parity = 0
-        self.last = RunStats()
+    def __init__(self, grid: TileGrid, filt: Filter, halo_depth: int | None = None,
+                 band: int | None = None):
+        from .fused_runtime import FusedRuntime
+        self.grid = grid
+        self.rt = FusedRuntime(grid, filt, 0, 1, None, halo_depth=halo_depth, band=band)
+        self.sms, self.bands = self.rt.sms, self.rt.bands
 
     def close(self) -> None:
-        for m in self.mems:
-            m.free()
-        self.mems = []
+        self.rt.close()
 
     def upload(self, image: np.ndarray) -> None:
         g = self.grid
         img = np.ascontiguousarray(image, dtype=np.uint8).reshape(g.height, g.row_bytes)
-        for d in self.drivers:
-            t = d.tile
-            d.upload(img[t.row0:t.row0 + t.rows, t.col0 * g.channels:(t.col0 + t.cols) * g.channels], 0)
-        self.parity = 0
+        Cn = g.channels
+        self.rt.upload({t.rank: img[t.row0:t.row0 + t.rows, t.col0 * Cn:(t.col0 + t.cols) * Cn]
+                        for t in g.tiles()})
 
     def synth(self, seed: int) -> None:
-        for d in self.drivers:
-            d.synth(seed, 0)
-        self.parity = 0
+        self.rt.synth(seed)
 
     def download(self) -> np.ndarray:
-        g = self.grid
+        g, Cn = self.grid, self.grid.channels
         out = np.empty((g.height, g.row_bytes), dtype=np.uint8)
-        for d in self.drivers:
-            t = d.tile
-            out[t.row0:t.row0 + t.rows, t.col0 * g.channels:(t.col0 + t.cols) * g.channels] = \
-                d.download(self.parity)
+        for r, tile in self.rt.download().items():
+            t = g.tile(r)
+            out[t.row0:t.row0 + t.rows, t.col0 * Cn:(t.col0 + t.cols) * Cn] = tile
         return out
 
-    def run(self, loops: int, plan: StreamPlan | None = None) -> RunStats:
+    def run(self, loops: int) -> RunStats:
         """Enqueue ``loops`` iterations (asynchronous; ``download`` synchronises)."""
-        stats = RunStats()
-        if loops <= 0:
-            self.last = stats
-            return stats
-        plan = plan or make_plan(self.grid, self.filt, loops, self.halo_depth, self.sms, self.bands)
-        stats.plan = plan
-        multi = self.use_flags and self.grid.workers > 1
-        for d in self.drivers:
+        for d in self.rt.drivers.values():
             d.reset_status()
-        for i, k in enumerate(plan.launches(loops)):
-            for d in self.drivers:
-                d.enqueue(plan, k, self.parity, first=(i == 0), multi=multi)
-            self.parity ^= 1
-            stats.launches += len(self.drivers)
-        self.last = stats
-        return stats
+        plan, launches = self.rt.enqueue(loops)
+        self.last = RunStats(launches=launches, plan=plan)
+        return self.last
 
     def collect_status(self) -> RunStats:
         s = self.last
-        for d in self.drivers:
+        for d in self.rt.drivers.values():
             err, mx, sm, n = d.read_status()
             s.watchdog |= err
             s.max_wait_us = max(s.max_wait_us, mx)

@@ -1,0 +1,167 @@
+"""FusedRuntime: the per-process driver of the fused backend.
+
+Unifies the two process models behind one interface used by ``ConvEngine``:
+
+* single process — ``world == 1``: this process owns every tile of the grid as *virtual ranks* on
+  one device (1 tile for a plain single-GPU run);
+* one process per GPU — ``world > 1``: this process owns tile ``rank`` and maps its neighbours'
+  buffers through CUDA IPC (``peer_memory.PeerGroup``).
+
+A run is enqueued with ONE native call (``pconv_stream_run``): all launches of all local tiles go
+onto one stream back to back; cross-rank ordering is entirely in-kernel (epoch flags). The host
+synchronises twice per run (before: inputs in place; after: results readable), never in between.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ..models.filters import Filter
+from ..ops import cuda as K
+from .decomposition import TileGrid
+from .fused import RankMemory, STATUS_WORDS, TileDriver, make_plan, tile_pitch
+from .plan import StreamPlan
+
+
+class FusedRuntime:
+    def __init__(self, grid: TileGrid, filt: Filter, rank: int, world: int, dist,
+                 halo_depth: int | None = None, mode: str = "auto", timeout_ms: float = 10_000.0,
+                 band: int | None = None):
+        self.grid, self.filt, self.rank, self.world, self.dist = grid, filt, rank, world, dist
+        self.halo_depth, self.mode, self.band = halo_depth, mode, band
+        self.pitch = tile_pitch(grid)
+        self.stream = K.stream_create()
+        self.sms = K.sm_count()
+        self.bands = K.band_heights(filt.kind)
+        rows = grid.max_tile_rows()
+        self.peers = None
+        if world > 1:
+            if grid.workers != world:
+                raise ValueError("one tile per process: grid size must equal the world size")
+            from .peer_memory import PeerGroup
+            self.local_ranks = [rank]
+            mem = RankMemory.allocate(rows, self.pitch)
+            self.mems = {rank: mem}
+            self.peers = PeerGroup(rank, world)
+            nbrs = {rank: self.peers.exchange(mem, grid.neighbors(rank))}
+        else:
+            self.local_ranks = list(range(grid.workers))
+            self.mems = {r: RankMemory.allocate(rows, self.pitch) for r in self.local_ranks}
+            nbrs = {r: [self.mems[n] if n >= 0 else None for n in grid.neighbors(r)]
+                    for r in self.local_ranks}
+        self.drivers = {r: TileDriver(grid, r, filt, self.mems[r], nbrs[r], self.pitch, self.stream,
+                                      timeout_ms) for r in self.local_ranks}
+        self.parity = 0
+        self.epoch = 0
+        self.multi = grid.workers > 1
+        self._plans: dict[int, StreamPlan] = {}
+
+    # -- lifecycle ------------------------------------------------------------------------------
+    def close(self) -> None:
+        K.stream_sync(self.stream)
+        if self.peers is not None:
+            K.device_sync()
+            self.peers.barrier()      # nobody may still be reading my buffers
+            self.peers.close()
+        for m in self.mems.values():
+            m.free()
+        self.mems = {}
+        K.stream_destroy(self.stream)
+
+    def _barrier(self) -> None:
+        if self.peers is not None:
+            K.stream_sync(self.stream)
+            self.peers.barrier()
+
+    # -- data -----------------------------------------------------------------------------------
+    def upload(self, tiles: dict[int, np.ndarray]) -> None:
+        self._barrier()               # previous run's readers are done with my buffers
+        for r, tile in tiles.items():
+            self.drivers[r].upload(tile, 0)
+        self.parity = 0
+
+    def synth(self, seed: int) -> None:
+        self._barrier()
+        for d in self.drivers.values():
+            d.synth(seed, 0)
+        self.parity = 0
+
+    def download(self) -> dict[int, np.ndarray]:
+        return {r: d.download(self.parity) for r, d in self.drivers.items()}
+
+    def buffer_ptr(self, rank: int, parity: int | None = None) -> int:
+        return self.mems[rank].bufs[self.parity if parity is None else parity]
+
+    # -- compute ----------------------------------------------------------------------------------
+    def plan(self, loops: int) -> StreamPlan:
+        if loops not in self._plans:
+            self._plans[loops] = make_plan(self.grid, self.filt, loops, self.halo_depth, self.sms,
+                                           self.bands, self.band)
+        return self._plans[loops]
+
+    # -- in-stream input hand-over (no host barrier between back-to-back steps) -------------------
+    def _sync_params(self, d: TileDriver, wait: int, signal: int) -> K.Sync:
+        p = d._params(self.plan(1), 1, 0, wait, signal)
+        return p.sync
+
+    def begin_input(self) -> int:
+        """Enqueue: wait until every neighbour finished the previous run (they may still be reading
+        my buffers). Call before overwriting a tile buffer in-stream. Returns kernels launched."""
+        if not self.multi or self.epoch == 0:
+            return 0
+        for d in self.drivers.values():
+            K.sync_launch(self._sync_params(d, self.epoch, 0), self.stream)
+        return len(self.drivers)
+
+    def end_input(self) -> int:
+        """Enqueue: announce "my input tile is in place"; the next run's first launch waits for it."""
+        if not self.multi:
+            return 0
+        self.epoch += 1
+        for d in self.drivers.values():
+            K.sync_launch(self._sync_params(d, 0, self.epoch), self.stream)
+        self._first_wait = self.epoch
+        return len(self.drivers)
+
+    def enqueue(self, loops: int) -> tuple[StreamPlan | None, int]:
+        """Enqueue ``loops`` iterations on the runtime stream; returns (plan, kernel launches)."""
+        if loops <= 0:
+            return None, 0
+        plan = self.plan(loops)
+        ks = plan.launches(loops)
+        n = len(self.local_ranks)
+        blocks = (K.StreamParams * (2 * n))()
+        for i, r in enumerate(self.local_ranks):
+            d = self.drivers[r]
+            blocks[2 * i] = d._params(plan, plan.k, self.parity, 0, 0)
+            blocks[2 * i + 1] = d._params(plan, plan.k, self.parity ^ 1, 0, 0)
+        first_wait, self._first_wait = getattr(self, "_first_wait", 0), 0
+        K.stream_run(blocks, n, ks, self.epoch, self.multi, self.stream, first_wait)
+        self.epoch += len(ks)
+        self.parity ^= len(ks) & 1
+        return plan, len(ks) * n
+
+    def run(self, loops: int, rep, sync: bool = True) -> None:
+        for d in self.drivers.values():
+            d.reset_status()
+        self._barrier()               # every rank's input tile is in place
+        e0, e1 = K.Event(), K.Event()
+        e0.record(self.stream)
+        plan, launches = self.enqueue(loops)
+        e1.record(self.stream)
+        rep.launches = launches
+        rep.plan = dict(plan.__dict__) if plan else {}
+        if not sync:
+            self._pending = (e0, e1)
+            return
+        e1.synchronize()
+        rep.elapsed_ms = e0.elapsed_ms(e1)
+        for d in self.drivers.values():
+            err, mx, sm, nw = d.read_status()
+            rep.watchdog |= err
+            rep.max_wait_us = max(rep.max_wait_us, mx)
+            rep.sum_wait_us += sm
+            rep.waits += nw
+        self._barrier()
+        if rep.watchdog:
+            raise RuntimeError("halo watchdog fired: a neighbouring rank never signalled "
+                               f"(timeout {self.drivers[self.local_ranks[0]].timeout_ns / 1e6:.0f} ms)")

@@ -26,17 +26,17 @@ def main():
     a = ap.parse_args()
     f = Filter.parse(a.filter)
     g = TileGrid.create(a.height, a.width, a.channels, a.workers)
-    vc = VirtualCluster(g, f, halo_depth=a.k or None)
+    vc = VirtualCluster(g, f, halo_depth=a.k or None, band=a.band or None)
     vc.synth(1)
-    plan = make_plan(g, f, a.loops, a.k or None, vc.sms, vc.bands, a.band or None)
-    vc.run(a.loops, plan)
+    plan = vc.rt.plan(a.loops)
+    vc.run(a.loops)
     K.device_sync()
     best = 1e9
     for _ in range(a.reps):
         e0, e1 = K.Event(), K.Event()
-        e0.record(0)
-        vc.run(a.loops, plan)
-        e1.record(0)
+        e0.record(vc.rt.stream)
+        vc.run(a.loops)
+        e1.record(vc.rt.stream)
         e1.synchronize()
         best = min(best, e0.elapsed_ms(e1))
     mpx = a.width * a.height * a.loops / (best * 1e-3) / 1e6
