@@ -92,11 +92,17 @@ def build_cuda(force: bool = False) -> Path:
         return CUDA_LIB
     if not Path(NVCC).exists():
         raise RuntimeError(f"nvcc not found at {NVCC}; the CUDA library cannot be built")
-    objs = []
-    for s in srcs:
+    from concurrent.futures import ThreadPoolExecutor
+    hdrs = _all_headers()
+
+    def compile_one(s: Path) -> str:
         o = LIB / (s.stem + ".cu.o")
-        _run([NVCC, *NVCCFLAGS, "-c", str(s), "-o", str(o)], log=LIB / (s.stem + ".ptxas.log"))
-        objs.append(str(o))
+        if force or _stale(o, [s] + hdrs):
+            _run([NVCC, *NVCCFLAGS, "-c", str(s), "-o", str(o)], log=LIB / (s.stem + ".ptxas.log"))
+        return str(o)
+
+    with ThreadPoolExecutor(max_workers=min(4, len(srcs))) as ex:   # the kernel TUs take minutes
+        objs = list(ex.map(compile_one, srcs))
     _run([NVCC, "-ccbin", CXX, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(CUDA_LIB),
           *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     return CUDA_LIB

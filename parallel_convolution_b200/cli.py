@@ -1,0 +1,193 @@
+"""Command line: drop-in for the reference programs, plus the options they never had.
+
+Reference grammar (``mpi/mpi_conv.c:340-360``, ``cuda/funcs.c:10-29``), kept verbatim::
+
+    pconv image width height loops {rgb|grey}
+
+* single process:           ``python -m parallel_convolution_b200 img.raw 1920 2520 50 grey``
+  (the reference's ``./cuda_conv ...``; add ``--backend cpu`` for a GPU-less box)
+* one process per GPU:       ``torchrun --standalone --local-addr 127.0.0.1 --nproc-per-node 8 -m
+  parallel_convolution_b200 img.raw 1920 2520 50 rgb`` (the reference's ``mpirun -np 8 ./mpi_conv``)
+* CPU ranks over gloo:       same with ``--backend cpu`` (``mpi_conv`` / ``mpi_omp_conv --threads T``)
+
+Output: ``blur_<basename>`` next to the input (``-o`` overrides) and the elapsed seconds of the
+iteration loop on stdout, max over ranks (``mpi/mpi_conv.c:273-283`` prints ``%f\\n``); ``--json``
+prints a machine-readable report instead. Errors are reported with a message and a non-zero exit,
+never by hanging (the reference spins forever on a short file, ``cuda/funcs.c:39-45``).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+from .utils import checkpoint as ckpt
+from .utils.nvtx import nvtx_range
+
+USAGE_HINT = "image_name width height loops [rgb/grey]"
+
+
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(prog="pconv", description=__doc__,
+                                formatter_class=argparse.RawDescriptionHelpFormatter)
+    p.add_argument("image", help="raw headerless image (or any name with --synthetic)")
+    p.add_argument("width", type=int)
+    p.add_argument("height", type=int)
+    p.add_argument("loops", type=int)
+    p.add_argument("color", choices=["rgb", "grey", "gray"])
+    p.add_argument("--filter", default="gaussian",
+                   help="builtin name (box, gaussian, edge, sharpen, laplacian, emboss, sobel_x, sobel_y, "
+                        "identity), 'a,b,c,d,e,f,g,h,i[/div]', nine floats, or a file")
+    p.add_argument("--backend", default="auto", choices=["auto", "fused", "nccl", "cpu", "host"])
+    p.add_argument("--mode", default="auto", choices=["auto", "stream", "resident"],
+                   help="fused backend: persistent on-chip kernel vs streaming launches")
+    p.add_argument("--gpus", "--workers", dest="workers", type=int, default=None,
+                   help="single process: decompose over N virtual ranks on one GPU")
+    p.add_argument("--grid", default=None, help="tile grid ROWSxCOLS (default: perimeter-minimising)")
+    p.add_argument("--halo-depth", type=int, default=None, help="temporal-blocking depth k")
+    p.add_argument("--threads", type=int, default=0, help="cpu backend: OpenMP threads per rank")
+    p.add_argument("-o", "--output", default=None)
+    p.add_argument("--no-output", action="store_true", help="skip writing the result image")
+    p.add_argument("--synthetic", type=int, default=None, metavar="SEED",
+                   help="ignore the input file; generate a random image per tile")
+    p.add_argument("--json", action="store_true", help="print a JSON report instead of the seconds")
+    p.add_argument("--checkpoint-every", type=int, default=0, metavar="K",
+                   help="write the state image + JSON sidecar every K iterations")
+    p.add_argument("--resume", action="store_true", help="continue from the checkpoint of this output")
+    p.add_argument("--verify", action="store_true",
+                   help="recompute on the CPU oracle engine and compare byte for byte (small images)")
+    p.add_argument("--timeout-ms", type=float, default=10_000.0, help="in-kernel halo watchdog")
+    p.add_argument("--inject-drop-signal", type=int, default=None, metavar="RANK",
+                   help="fault injection: RANK never signals its neighbours (watchdog demo)")
+    return p
+
+
+def _init_dist(backend: str):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if backend in ("cpu", "host") or not torch.cuda.is_available():
+        dist.init_process_group("gloo")
+    else:
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist
+
+
+def main(argv: list[str] | None = None) -> int:
+    parser = build_parser()
+    try:
+        a = parser.parse_args(argv)
+    except SystemExit as e:
+        if e.code not in (0, None):
+            sys.stderr.write(f"\nError Input!\n{parser.prog} {USAGE_HINT}\n\n")
+        raise
+    if a.width <= 0 or a.height <= 0 or a.loops < 0:
+        sys.stderr.write("width and height must be positive, loops non-negative\n")
+        return 2
+    channels = 3 if a.color == "rgb" else 1
+    grid = tuple(int(v) for v in a.grid.lower().split("x")) if a.grid else None
+    dist = _init_dist(a.backend)
+    rank = dist.get_rank() if dist else 0
+
+    from .engine import ConvEngine
+    out_path = a.output
+    if out_path is None:
+        d, b = os.path.split(a.image)
+        out_path = os.path.join(d, "blur_" + b)
+    try:
+        with nvtx_range("pconv:setup"):
+            eng = ConvEngine(width=a.width, height=a.height, channels=channels, filter=a.filter,
+                             backend=a.backend, workers=a.workers, grid=grid, halo_depth=a.halo_depth,
+                             mode=a.mode, threads=a.threads, timeout_ms=a.timeout_ms)
+        if a.inject_drop_signal is not None and hasattr(eng._impl, "drivers"):
+            for r, d in eng._impl.drivers.items():
+                d.inject_drop_signal = (r == a.inject_drop_signal)
+        done = 0
+        with nvtx_range("pconv:load"):
+            state = ckpt.load_state(out_path) if a.resume else None
+            if state is not None:
+                ckpt.check_compatible(state, a.width, a.height, channels, eng.filter, a.loops)
+                eng.load_file(ckpt.image_path(out_path))
+                done = state["iterations_done"]
+            elif a.synthetic is not None:
+                eng.load_synthetic(a.synthetic)
+            else:
+                eng.load_file(a.image)
+        elapsed_ms, launches, rep = 0.0, 0, None
+        with nvtx_range("pconv:iterate"):
+            while done < a.loops or rep is None:
+                n = a.loops - done
+                if a.checkpoint_every > 0:
+                    n = min(n, a.checkpoint_every)
+                rep = eng.iterate(n)
+                elapsed_ms += rep.elapsed_ms
+                launches += rep.launches
+                done += n
+                if a.checkpoint_every > 0 and done < a.loops:
+                    ckpt.save_state(eng, out_path, done, a)
+                if n == 0:
+                    break
+        if not a.no_output:
+            with nvtx_range("pconv:store"):
+                eng.save_file(out_path)
+                if rank == 0:
+                    ckpt.clear_state(out_path)
+        verified = None
+        if a.verify:
+            verified = _verify(eng, a, channels, out_path)
+        if rank == 0:
+            if a.json:
+                g = eng.grid
+                mpx = a.width * a.height * a.loops / max(elapsed_ms, 1e-9) / 1e3
+                print(json.dumps({
+                    "seconds": elapsed_ms / 1e3, "mpixels_per_s": mpx, "iterations": a.loops,
+                    "backend": eng.backend, "filter": eng.filter.describe(), "grid": g.describe(),
+                    "workers": g.workers, "plan": rep.plan, "kernel_launches": launches,
+                    "exposed_halo_wait_us": {"max": rep.max_wait_us, "sum": rep.sum_wait_us, "waits": rep.waits},
+                    "halo_bytes_per_exchange_rank0": g.halo_bytes_per_iteration(0, rep.plan.get("k", 1) or 1),
+                    "output": None if a.no_output else out_path, "verified": verified}))
+            else:
+                print(f"{elapsed_ms / 1e3:f}")
+        eng.close()
+    except (OSError, ValueError, RuntimeError) as e:
+        sys.stderr.write(f"pconv: {e}\n")
+        if dist:
+            try:
+                dist.destroy_process_group()
+            except Exception:
+                pass
+        return 1
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0 if verified in (None, True) else 3
+
+
+def _verify(eng, a, channels: int, out_path: str) -> bool | None:
+    """Rank 0 recomputes the whole image on the CPU engine and compares with the gathered result."""
+    import numpy as np
+    from .ops import host as H
+    out = eng.gather()
+    if eng.rank != 0:
+        return None
+    rb = a.width * channels
+    if a.synthetic is not None:
+        src = H.synth_rect(a.synthetic, rb, 0, a.height, 0, rb)
+    else:
+        src = H.read_rect(ckpt.original_input(a.image), rb, 0, a.height, 0, rb)
+    img = src.reshape(a.height, a.width, channels) if channels > 1 else src
+    ref = H.cpu_run_image(img, eng.filter.spec, a.loops, a.threads)
+    same = bool(np.array_equal(ref.reshape(out.shape), out))
+    if not same:
+        sys.stderr.write(f"pconv: VERIFY FAILED: {(ref.reshape(out.shape) != out).sum()} bytes differ\n")
+    return same
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -72,29 +72,32 @@ int pconv_sync_launch(const pconv_sync_t* s, void* stream);
 // Band heights compiled for a filter kind; returns the count, fills out[0..cap).
 int pconv_stream_band_heights(int kind, int* out, int cap);
 
-// ---- resident kernel: the whole tile stays in shared memory for all iterations -----------------
+// ---- resident kernel: the whole tile stays in registers for ALL iterations of a run ------------
+// One persistent launch: CTA (ti,tj) keeps its region in registers, and every k iterations the CTAs
+// exchange k-deep border strips through the (L2-resident / peer-mapped) tile buffers with per-CTA
+// epoch flags — between CTAs of one GPU and, for border CTAs, straight across NVLink.
+// Requires nty*ntx <= #SMs (all CTAs co-resident; launched cooperatively) and identical tile
+// shapes on every rank.
 typedef struct pconv_resident_params {
     pconv_geometry_t g;
-    const uint8_t* src[9];   // iteration-0 image AND halo exchange buffer, parity 0 (per direction)
-    const uint8_t* alt[9];   // halo exchange buffer, parity 1 (per direction)
-    uint8_t* self_src;       // == src[4], writable
-    uint8_t* self_alt;       // == alt[4], writable
-    uint8_t* dst;            // final result (may alias self_src / self_alt)
+    const uint8_t* src_a[9]; // parity-0 buffers by direction: the input image, then even exchanges
+    const uint8_t* src_b[9]; // parity-1 buffers by direction: odd exchanges
+    uint8_t* self_a;         // == src_a[4], writable
+    uint8_t* self_b;         // == src_b[4], writable
     pconv_filter_t filt;
-    int32_t loops;           // total iterations
-    int32_t k;               // iterations between halo exchanges
-    int32_t TH, TWB, HB;     // region interior / halo geometry (as above)
-    int32_t nty, ntx;        // CTA grid; nty*ntx CTAs must be co-resident
-    uint32_t* cta_flags;     // [(nty+2)*(ntx+2)] epoch flags incl. a ring mirrored from neighbours
+    int32_t loops;           // total iterations in this launch (>= 1)
+    int32_t k;               // iterations between exchanges
+    int32_t TH, TWB, HB;     // region interior / halo geometry (as in the stream kernel)
+    int32_t R;               // band height
+    int32_t nty, ntx;        // CTA grid (same on every rank)
+    uint32_t* cta_flags;     // [(nty+2)*(ntx+2)] epochs, incl. a ring mirrored from neighbour GPUs
     uint32_t* remote_cta_flags[9];  // the same array on neighbour d (peer-mapped) or NULL
-    uint32_t epoch_base;     // flags are compared against epoch_base + exchange index
+    uint32_t epoch_base;     // exchange b (1-based) uses epoch_base + b; host advances it per run
     uint32_t pad_;
-    uint64_t timeout_ns;
-    uint64_t* status;
+    pconv_sync_t sync;       // launch-level protocol, identical to the stream kernel's
 } pconv_resident_params_t;
-
+// The result lands in parity (ceil(loops/k) & 1): 1 -> self_b, 0 -> self_a.
 int pconv_resident_launch(const pconv_resident_params_t* p, void* stream);
-int pconv_resident_max_region_rows(void);
 
 // ---- runtime -----------------------------------------------------------------------------------
 int pconv_cuda_device_count(void);

@@ -30,7 +30,7 @@ __device__ __forceinline__ int owner_of(int64_t v, const int64_t (&lo)[4]) {
 // Slow path of load_chunk: a chunk that straddles an ownership boundary / the image edge, or is
 // misaligned in its owner's buffer, is assembled byte by byte. Kept out of line: it is rare (only
 // odd tile widths hit it) and would otherwise be unrolled into every band row.
-__device__ __noinline__ uint4 load_chunk_bytes(const pconv_geometry_t& g, const SourceSet& s,
+static __device__ __noinline__ uint4 load_chunk_bytes(const pconv_geometry_t& g, const SourceSet& s,
                                                int orow, int64_t lrow, int64_t gb) {
     uint32_t w[4] = {0u, 0u, 0u, 0u};
     for (int t = 0; t < 16; ++t) {
@@ -67,6 +67,39 @@ __device__ __forceinline__ uint4 load_chunk(const pconv_geometry_t& g, const Sou
         }
     }
     return load_chunk_bytes(g, s, orow, lrow, gb);
+}
+
+// Load R consecutive rows of one 16-byte column strip (a warp's band) into registers. The column
+// classification (owner, offset, fast/slow) is done once; per row only the owning tile-row is
+// selected, so the common case costs a compare, a 64-bit multiply-add and one 128-bit load.
+template <int R>
+__device__ __forceinline__ void load_band(uint4 (&rows)[R], const pconv_geometry_t& g,
+                                          const SourceSet& s, int64_t gr0, int64_t gb) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const bool col_out = gb + 16 <= 0 || gb >= g.img_cb;
+    const bool col_whole = gb >= 0 && gb + 16 <= g.img_cb;
+    const int oc = owner_of(gb < 0 ? 0 : gb, g.cb_lo);
+    const bool fast = col_whole && owner_of(gb + 15, g.cb_lo) == oc;
+    // per owning tile-row: pointer to (image row 0 of that tile, my column) and its pitch
+    const uint8_t* bp[3];
+    int64_t pp[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        const int d = o * 3 + oc;
+        pp[o] = s.pitch[d];
+        bp[o] = s.p[d] ? s.p[d] + (gb - g.cb_lo[oc]) - g.row_lo[o] * pp[o] : nullptr;
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int64_t gr = gr0 + i;
+        if (col_out || gr < 0 || gr >= g.img_rows) { rows[i] = z; continue; }
+        const int o = owner_of(gr, g.row_lo);
+        const uint8_t* a = bp[o] + gr * pp[o];
+        if (fast && bp[o] != nullptr && (reinterpret_cast<uintptr_t>(a) & 15u) == 0)
+            rows[i] = __ldcg(reinterpret_cast<const uint4*>(a));
+        else
+            rows[i] = load_chunk_bytes(g, s, o, gr - g.row_lo[o], gb);
+    }
 }
 
 // Store one 16-byte chunk at image position (gr, gb) into my tile, clipped to the tile.
@@ -112,6 +145,14 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t atom_add_acq_rel_gpu(uint32_t* p, uint32_t v) {
     uint32_t old;
     asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
@@ -125,13 +166,17 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 
 // Spin until *flag >= want (epochs are monotonically increasing, wrap-safe compare) or the
 // watchdog fires. Returns the ns spent waiting; on timeout records error 1 in status[0].
+// SYS: the flag is written by another GPU (system scope); otherwise by a CTA of this GPU (gpu
+// scope — an order of magnitude cheaper than a system-scope acquire/fence).
+template <bool SYS = true>
 __device__ __forceinline__ uint64_t wait_flag(const uint32_t* flag, uint32_t want,
                                               uint64_t timeout_ns, uint64_t* status) {
-    if ((int32_t)(ld_acquire_sys(flag) - want) >= 0) return 0;
+    auto ld = [&]() { return SYS ? ld_acquire_sys(flag) : ld_acquire_gpu(flag); };
+    if ((int32_t)(ld() - want) >= 0) return 0;
     const uint64_t t0 = globaltimer_ns();
     uint64_t dt = 0;
-    while ((int32_t)(ld_acquire_sys(flag) - want) < 0) {
-        __nanosleep(64);
+    while ((int32_t)(ld() - want) < 0) {
+        __nanosleep(32);
         dt = globaltimer_ns() - t0;
         if (dt > timeout_ns) {
             if (status) atomicExch(reinterpret_cast<unsigned long long*>(status), 1ull);

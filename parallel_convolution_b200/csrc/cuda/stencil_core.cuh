@@ -71,7 +71,7 @@ __device__ __forceinline__ uint32_t lanes_shift(uint32_t a, uint32_t b) { return
 // Sep121Path — the reference's default Gaussian (mpi/mpi_conv.c:96,104; cuda_convolute.cu:12).
 // Exactness: every partial sum is an integer <= 4080 < 2^16, result = sum >> 4.
 //   vertical   V_r(x)  = p_{r-1}(x) + 2 p_r(x) + p_{r+1}(x)  as (U_{r-1}+U_r) + (U_r+U_{r+1})
-//   horizontal out(x)  = V(x-C) + 2 V(x) + V(x+C)            as  s(x-C) + s(x),  s(x) = V(x)+V(x+C)
+//   horizontal out(x)  = V(x-C) + 2 V(x) + V(x+C)            on the 16-bit V lanes
 // =============================================================================================
 template <int C>
 struct Sep121Path {
@@ -100,7 +100,7 @@ struct Sep121Path {
     // push row r+1, return output row r
     __device__ __forceinline__ uint4 push(const uint4& w) {
         const uint32_t x[4] = {w.x, w.y, w.z, w.w};
-        uint32_t vE[5], vO[5];
+        uint32_t vE[4], vO[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t nE = lanes_even(x[j]), nO = lanes_odd(x[j]);
@@ -108,36 +108,36 @@ struct Sep121Path {
             vE[j] = pE[j] + qE; vO[j] = pO[j] + qO;           // V_r  (<= 1020 per lane)
             pE[j] = qE; pO[j] = qO; uE[j] = nE; uO[j] = nO;
         }
+        // Horizontal pass straight on the V lanes. vX[0] is the left neighbour lane's word 3,
+        // vX[1..4] this lane's words, vX[5] the right neighbour lane's word 0: the shuffles only
+        // depend on V, so all of them are in flight before any horizontal arithmetic starts.
+        //   grey (C=1): out(x) = V(x-1) + 2V(x) + V(x+1)      RGB (C=3): out(x) = V(x-3) + 2V(x) + V(x+3)
+        // The sums (<= 4080) are shifted LEFT by 4 (<= 65280, still inside the 16-bit lane) so the
+        // result byte is the lane's high byte and one PRMT packs four of them: no masks, and the
+        // shifts run on the FMA pipe (IMAD.SHL), which the profile shows is the idle one.
         uint32_t o[4];
         if (C == 1) {
-            vE[4] = __shfl_down_sync(kFull, vE[0], 1);  // right neighbour's first even lanes
-            uint32_t so[5];                              // so[j+1] = SO_j = (s(4j+3), s(4j+1))
-#pragma unroll
-            for (int j = 0; j < 4; ++j) so[j + 1] = vO[j] + lanes_shift(vE[j], vE[j + 1]);
-            so[0] = __shfl_up_sync(kFull, so[4], 1);    // left neighbour's last SO
+            const uint32_t oL = __shfl_up_sync(kFull, vO[3], 1);    // V(x-1) for this lane's byte 0
+            const uint32_t eR = __shfl_down_sync(kFull, vE[0], 1);  // V(x+1) for this lane's byte 15
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint32_t se = vE[j] + vO[j];                       // (s(4j+2), s(4j))
-                const uint32_t oE = se + lanes_shift(so[j], so[j + 1]);  // s(x-1) + s(x), even x
-                const uint32_t oO = se + so[j + 1];                      // odd x
-                o[j] = ((oE >> 4) & 0x00ff00ffu) | ((oO << 4) & 0xff00ff00u);
+                const uint32_t oPrev = j ? vO[j - 1] : oL, eNext = j < 3 ? vE[j + 1] : eR;
+                const uint32_t oE = 2u * vE[j] + lanes_shift(oPrev, vO[j]) + vO[j];
+                const uint32_t oO = 2u * vO[j] + vE[j] + lanes_shift(vE[j], eNext);
+                o[j] = prmt(oE << 4, oO << 4, 0x7351u);
             }
         } else {
-            vE[4] = __shfl_down_sync(kFull, vE[0], 1);
-            vO[4] = __shfl_down_sync(kFull, vO[0], 1);
-            uint32_t se[5], so[5];  // index j+1 holds word j; index 0 is the left neighbour's word 3
+            const uint32_t eL = __shfl_up_sync(kFull, vE[3], 1), oL = __shfl_up_sync(kFull, vO[3], 1);
+            const uint32_t eR = __shfl_down_sync(kFull, vE[0], 1), oR = __shfl_down_sync(kFull, vO[0], 1);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                se[j + 1] = vE[j] + lanes_shift(vO[j], vO[j + 1]);  // (s3(4j+2), s3(4j))
-                so[j + 1] = vO[j] + vE[j + 1];                      // (s3(4j+3), s3(4j+1))
-            }
-            se[0] = __shfl_up_sync(kFull, se[4], 1);
-            so[0] = __shfl_up_sync(kFull, so[4], 1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t oE = se[j + 1] + so[j];                           // s3(x-3)+s3(x), even x
-                const uint32_t oO = so[j + 1] + lanes_shift(se[j], se[j + 1]);   // odd x
-                o[j] = ((oE >> 4) & 0x00ff00ffu) | ((oO << 4) & 0xff00ff00u);
+                const uint32_t ePrev = j ? vE[j - 1] : eL, oPrev = j ? vO[j - 1] : oL;
+                const uint32_t eNext = j < 3 ? vE[j + 1] : eR, oNext = j < 3 ? vO[j + 1] : oR;
+                // even x = 4j, 4j+2: x-3 -> (4j-3, 4j-1) = O lanes of word j-1; x+3 -> (4j+3, 4j+5)
+                const uint32_t oE = 2u * vE[j] + oPrev + lanes_shift(vO[j], oNext);
+                // odd x = 4j+1, 4j+3: x-3 -> (4j-2, 4j); x+3 -> (4j+4, 4j+6) = E lanes of word j+1
+                const uint32_t oO = 2u * vO[j] + lanes_shift(ePrev, vE[j]) + eNext;
+                o[j] = prmt(oE << 4, oO << 4, 0x7351u);
             }
         }
         return make_uint4(o[0], o[1], o[2], o[3]);

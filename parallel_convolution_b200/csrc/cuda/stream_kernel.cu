@@ -83,8 +83,7 @@ stream_kernel(const __grid_constant__ StreamArgs A) {
         const int64_t grw = gr0 + (int64_t)warp * R;   // image row of my band row 0
         const int64_t gb = gb0 + 16 * lane;            // image byte of my strip
         uint4 rows[R];
-#pragma unroll
-        for (int i = 0; i < R; ++i) rows[i] = load_chunk(g, A.src, grw + i, gb);
+        load_band<R>(rows, g, A.src, grw, gb);
 
         bool need_cols;
         const uint4 cmask = column_mask(g, gb0, &need_cols);
@@ -112,7 +111,7 @@ stream_kernel(const __grid_constant__ StreamArgs A) {
     if (A.sync.signal_value != 0u) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence_system();
+            __threadfence();   // gpu scope; the last CTA's system fence below is cumulative
             const uint32_t ticket = atom_add_acq_rel_gpu(A.sync.done_counter, 1u);
             if (ticket == gridDim.x - 1) {
                 *A.sync.done_counter = 0u;  // self-reset for the next launch (stream ordered)

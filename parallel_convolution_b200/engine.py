@@ -63,6 +63,9 @@ class RunReport:
 
 
 def _dist():
+    import sys
+    if "torch.distributed" not in sys.modules:
+        return None      # never imported => cannot be initialised; keeps CPU/CLI start-up torch-free
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():

@@ -39,13 +39,12 @@ class StreamParams(C.Structure):
 
 
 class ResidentParams(C.Structure):
-    _fields_ = [("g", Geometry), ("src", C.c_void_p * 9), ("alt", C.c_void_p * 9),
-                ("self_src", C.c_void_p), ("self_alt", C.c_void_p), ("dst", C.c_void_p),
-                ("filt", FilterSpec), ("loops", C.c_int32), ("k", C.c_int32),
-                ("TH", C.c_int32), ("TWB", C.c_int32), ("HB", C.c_int32),
-                ("nty", C.c_int32), ("ntx", C.c_int32), ("cta_flags", C.c_void_p),
-                ("remote_cta_flags", C.c_void_p * 9), ("epoch_base", C.c_uint32),
-                ("pad_", C.c_uint32), ("timeout_ns", C.c_uint64), ("status", C.c_void_p)]
+    _fields_ = [("g", Geometry), ("src_a", C.c_void_p * 9), ("src_b", C.c_void_p * 9),
+                ("self_a", C.c_void_p), ("self_b", C.c_void_p), ("filt", FilterSpec),
+                ("loops", C.c_int32), ("k", C.c_int32), ("TH", C.c_int32), ("TWB", C.c_int32),
+                ("HB", C.c_int32), ("R", C.c_int32), ("nty", C.c_int32), ("ntx", C.c_int32),
+                ("cta_flags", C.c_void_p), ("remote_cta_flags", C.c_void_p * 9),
+                ("epoch_base", C.c_uint32), ("pad_", C.c_uint32), ("sync", Sync)]
 
 
 class CudaError(RuntimeError):

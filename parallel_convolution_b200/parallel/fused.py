@@ -27,6 +27,10 @@ from .plan import StreamPlan, plan_stream
 
 FLAG_BYTES = 256      # 9 x u32 flags + padding
 STATUS_WORDS = 4      # u64: error, max wait ns, sum wait ns, waits
+CTA_FLAG_BYTES = 4096  # resident kernel: (nty+2)*(ntx+2) u32 epochs, nty*ntx <= #SMs
+# control block layout (one cudaMalloc, one IPC handle): flags | counter | status | cta_flags
+OFF_COUNTER, OFF_STATUS, OFF_CTA = FLAG_BYTES, FLAG_BYTES + 64, FLAG_BYTES + 128
+CTL_BYTES = OFF_CTA + CTA_FLAG_BYTES
 
 
 def tile_pitch(grid: TileGrid) -> int:
@@ -45,13 +49,19 @@ class RankMemory:
     status: int = 0
     nbytes: int = 0
     owned: bool = True
+    cta_flags: int = 0
 
     @staticmethod
     def allocate(rows: int, pitch: int) -> "RankMemory":
         nbytes = rows * pitch + 256
         bufs = [K.malloc(nbytes), K.malloc(nbytes)]
-        ctl = K.malloc(FLAG_BYTES + 64 + 8 * STATUS_WORDS + 64)
-        return RankMemory(bufs, ctl, ctl + FLAG_BYTES, ctl + FLAG_BYTES + 64, nbytes, True)
+        ctl = K.malloc(CTL_BYTES)
+        return RankMemory(bufs, ctl, ctl + OFF_COUNTER, ctl + OFF_STATUS, nbytes, True, ctl + OFF_CTA)
+
+    @staticmethod
+    def view(bufs: list[int], ctl: int, nbytes: int) -> "RankMemory":
+        """Peer-mapped view of another rank's memory (same control-block layout)."""
+        return RankMemory(bufs, ctl, ctl + OFF_COUNTER, ctl + OFF_STATUS, nbytes, False, ctl + OFF_CTA)
 
     def free(self) -> None:
         if self.owned:
@@ -128,6 +138,31 @@ class TileDriver:
         p.sync.inject_drop_signal = 1 if self.inject_drop_signal else 0
         return p
 
+    def resident_params(self, plan: StreamPlan, loops: int, src_parity: int, wait: int, signal: int,
+                        cta_epoch: int) -> K.ResidentParams:
+        p = K.ResidentParams()
+        p.g = self._geom
+        for d in range(9):
+            nb = self.neighbors[d]
+            p.src_a[d] = nb.bufs[src_parity] if nb is not None else None
+            p.src_b[d] = nb.bufs[src_parity ^ 1] if nb is not None else None
+            remote = nb is not None and d != 4 and nb is not self.mem
+            p.remote_cta_flags[d] = nb.cta_flags if remote else None
+            p.sync.remote_flags[d] = (nb.flags + 4 * (8 - d)) if (nb is not None and d != 4) else None
+        p.self_a, p.self_b = self.mem.bufs[src_parity], self.mem.bufs[src_parity ^ 1]
+        p.filt = self.filt.spec
+        p.loops, p.k, p.TH, p.TWB, p.HB, p.R = loops, plan.k, plan.TH, plan.TWB, plan.HB, plan.R
+        p.nty, p.ntx = plan.nty, plan.ntx
+        p.cta_flags = self.mem.cta_flags
+        p.epoch_base = cta_epoch
+        p.sync.local_flags = self.mem.flags
+        p.sync.done_counter = self.mem.counter
+        p.sync.status = self.mem.status
+        p.sync.wait_value, p.sync.signal_value = wait, signal
+        p.sync.timeout_ns = self.timeout_ns
+        p.sync.inject_drop_signal = 1 if self.inject_drop_signal else 0
+        return p
+
     def enqueue(self, plan: StreamPlan, k: int, src_parity: int, first: bool,
                 multi: bool) -> None:
         """One launch of ``k`` fused iterations reading ``bufs[src_parity]``."""
@@ -172,6 +207,26 @@ class TileDriver:
         return bool(out[0]), float(out[1]) / 1e3, float(out[2]) / 1e3, int(out[3])
 
 
+def make_resident_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int | None = None,
+                       sms: int | None = None, bands: list[int] | None = None,
+                       band: int | None = None, peers: bool = False) -> StreamPlan | None:
+    """Plan for the persistent resident kernel, or None when the tile does not fit on chip."""
+    from .plan import plan_resident
+    if not grid.exact and grid.workers > 1:
+        return None      # the mirrored CTA-flag rings assume identical tile shapes on every rank
+    Cn = grid.channels
+    multi_r, multi_c = grid.grid_rows > 1, grid.grid_cols > 1
+    kw = {}
+    if sms:
+        kw["sms"] = sms
+    if bands:
+        kw["bands"] = bands
+    return plan_resident(grid.max_tile_rows(), grid.max_tile_cols() * Cn, Cn, filt.kind, max(loops, 1),
+                         min_nbr_rows=grid.min_tile_rows() if multi_r else None,
+                         min_nbr_cols=grid.min_tile_cols() if multi_c else None,
+                         force_k=halo_depth, force_R=band, peers=peers, **kw)
+
+
 def make_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int | None = None,
               sms: int | None = None, bands: list[int] | None = None,
               band: int | None = None) -> StreamPlan:
@@ -198,10 +253,11 @@ class VirtualCluster:
     """
 
     def __init__(self, grid: TileGrid, filt: Filter, halo_depth: int | None = None,
-                 band: int | None = None):
+                 band: int | None = None, mode: str = "stream", timeout_ms: float = 10_000.0):
         from .fused_runtime import FusedRuntime
         self.grid = grid
-        self.rt = FusedRuntime(grid, filt, 0, 1, None, halo_depth=halo_depth, band=band)
+        self.rt = FusedRuntime(grid, filt, 0, 1, None, halo_depth=halo_depth, band=band, mode=mode,
+                               timeout_ms=timeout_ms)
         self.sms, self.bands = self.rt.sms, self.rt.bands
 
     def close(self) -> None:

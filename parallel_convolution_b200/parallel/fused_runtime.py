@@ -18,7 +18,8 @@ import numpy as np
 from ..models.filters import Filter
 from ..ops import cuda as K
 from .decomposition import TileGrid
-from .fused import RankMemory, STATUS_WORDS, TileDriver, make_plan, tile_pitch
+from .fused import (RankMemory, STATUS_WORDS, TileDriver, make_plan, make_resident_plan,
+                    tile_pitch)
 from .plan import StreamPlan
 
 
@@ -52,8 +53,13 @@ class FusedRuntime:
                                       timeout_ms) for r in self.local_ranks}
         self.parity = 0
         self.epoch = 0
+        self.cta_epoch = 0            # resident kernel: per-CTA exchange epochs (monotonic)
         self.multi = grid.workers > 1
         self._plans: dict[int, StreamPlan] = {}
+        self._rplans: dict[int, StreamPlan | None] = {}
+        # virtual ranks in resident mode need their persistent kernels co-resident: one stream each
+        self._rank_streams = ({r: K.stream_create() for r in self.local_ranks}
+                              if len(self.local_ranks) > 1 else {})
 
     # -- lifecycle ------------------------------------------------------------------------------
     def close(self) -> None:
@@ -65,6 +71,8 @@ class FusedRuntime:
         for m in self.mems.values():
             m.free()
         self.mems = {}
+        for st in self._rank_streams.values():
+            K.stream_destroy(st)
         K.stream_destroy(self.stream)
 
     def _barrier(self) -> None:
@@ -122,10 +130,52 @@ class FusedRuntime:
         self._first_wait = self.epoch
         return len(self.drivers)
 
+    def resident_plan(self, loops: int) -> StreamPlan | None:
+        if loops not in self._rplans:
+            nloc = len(self.local_ranks)
+            self._rplans[loops] = make_resident_plan(
+                self.grid, self.filt, loops, self.halo_depth, self.sms // nloc, self.bands, self.band,
+                peers=self.world > 1)
+        return self._rplans[loops]
+
+    def choose_mode(self, loops: int) -> str:
+        if self.mode in ("stream", "resident"):
+            if self.mode == "resident" and self.resident_plan(loops) is None:
+                raise ValueError("resident mode requested but the tile does not fit on chip")
+            return self.mode
+        return "resident" if self.resident_plan(loops) is not None else "stream"
+
+    def _enqueue_resident(self, loops: int) -> tuple[StreamPlan, int]:
+        plan = self.resident_plan(loops)
+        nblocks = -(-loops // plan.k)
+        first_wait, self._first_wait = getattr(self, "_first_wait", 0), 0
+        signal = self.epoch + 1 if self.multi else 0
+        params = {r: self.drivers[r].resident_params(plan, loops, self.parity, first_wait if self.multi else 0,
+                                                     signal, self.cta_epoch) for r in self.local_ranks}
+        if self._rank_streams:
+            fork = K.Event().record(self.stream)
+            joins = []
+            for r, st in self._rank_streams.items():
+                K.stream_wait_event(st, fork)
+                K.resident_launch(params[r], st)
+                joins.append(K.Event().record(st))
+            for ev in joins:
+                K.stream_wait_event(self.stream, ev)
+            self._keep = (fork, joins)
+        else:
+            K.resident_launch(params[self.local_ranks[0]], self.stream)
+        if self.multi:
+            self.epoch += 1
+        self.cta_epoch += nblocks
+        self.parity ^= nblocks & 1
+        return plan, len(self.local_ranks)
+
     def enqueue(self, loops: int) -> tuple[StreamPlan | None, int]:
         """Enqueue ``loops`` iterations on the runtime stream; returns (plan, kernel launches)."""
         if loops <= 0:
             return None, 0
+        if self.choose_mode(loops) == "resident":
+            return self._enqueue_resident(loops)
         plan = self.plan(loops)
         ks = plan.launches(loops)
         n = len(self.local_ranks)

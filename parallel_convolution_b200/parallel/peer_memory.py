@@ -37,7 +37,6 @@ class PeerGroup:
     def exchange(self, mem: RankMemory, neighbors: list[int]) -> list[RankMemory | None]:
         """Export ``mem``, gather everybody's handles, map the neighbours. Collective."""
         mine = {"bufs": [K.ipc_export(p) for p in mem.bufs], "ctl": K.ipc_export(mem.flags),
-                "ctl_layout": (mem.counter - mem.flags, mem.status - mem.flags),
                 "nbytes": mem.nbytes}
         table: list[dict | None] = [None] * self.world
         self.dist.all_gather_object(table, mine)
@@ -54,8 +53,7 @@ class PeerGroup:
                     bufs = [K.ipc_open(b) for b in h["bufs"]]
                     ctl = K.ipc_open(h["ctl"])
                     self._opened += bufs + [ctl]
-                    off_c, off_s = h["ctl_layout"]
-                    cache[r] = RankMemory(bufs, ctl, ctl + off_c, ctl + off_s, h["nbytes"], owned=False)
+                    cache[r] = RankMemory.view(bufs, ctl, h["nbytes"])
                 views.append(cache[r])
         return views
 

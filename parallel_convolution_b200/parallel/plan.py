@@ -110,3 +110,51 @@ def plan_stream(tile_rows: int, tile_cb: int, C: int, kind: int, loops: int, *,
     if best is None:
         raise ValueError("no feasible stream plan (tile too small for any halo depth?)")
     return best[1]
+
+
+EXCHANGE_US = 3.0            # modelled cost of one in-kernel halo exchange (flags + strip traffic)
+EXCHANGE_US_PEER = 6.0       # ... when neighbours sit on other GPUs (NVLink round trips)
+
+
+def plan_resident(tile_rows: int, tile_cb: int, C: int, kind: int, loops: int, *,
+                  min_nbr_rows: int | None = None, min_nbr_cols: int | None = None,
+                  sms: int = DEFAULT_SMS, bands: list[int] | None = None, peers: bool = False,
+                  force_k: int | None = None, force_R: int | None = None) -> StreamPlan | None:
+    """Plan for the persistent resident kernel: the whole tile must fit the GPU's CTAs at once
+    (``ntx*nty <= sms``). Returns None when it does not (the caller streams instead)."""
+    loops = max(loops, 1)
+    bands = sorted(bands or DEFAULT_BANDS[kind])
+    if force_R:
+        bands = [force_R]
+    rate = BYTES_PER_CLK[kind] * CLOCK_GHZ * 1e3
+    kmax = min(loops, (WARPS * bands[-1] - 1) // 2, (REGION_BYTES // 2 - 64) // C)
+    if min_nbr_rows is not None:
+        kmax = min(kmax, min_nbr_rows)
+    if min_nbr_cols is not None:
+        kmax = min(kmax, min_nbr_cols)
+    kmax = max(kmax, 1)
+    ks = [force_k] if force_k else range(1, kmax + 1)
+    t_x = EXCHANGE_US_PEER if peers else EXCHANGE_US
+    best: tuple[float, StreamPlan] | None = None
+    for k in ks:
+        HB, TWB = region_geometry(k, C)
+        if TWB < max(64, HB):
+            continue
+        ntx = math.ceil(tile_cb / TWB)
+        for R in bands:
+            RH = WARPS * R
+            th_max = RH - 2 * k
+            if th_max < k:
+                continue
+            nty = math.ceil(tile_rows / th_max)
+            if ntx * nty > sms:
+                continue
+            TH = max(math.ceil(tile_rows / nty), k)
+            nblocks = math.ceil(loops / k)
+            t_block = k * RH * REGION_BYTES / rate
+            total = LAUNCH_US + (RH * REGION_BYTES + TH * TWB) / LOAD_BYTES_PER_US_PER_SM \
+                + nblocks * t_block + (nblocks - 1) * t_x
+            cand = StreamPlan(k, R, TH, TWB, HB, ntx, nty, 1, total)
+            if best is None or total < best[0] - 1e-9:
+                best = (total, cand)
+    return best[1] if best else None

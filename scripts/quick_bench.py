@@ -22,13 +22,14 @@ def main():
     ap.add_argument("--workers", type=int, default=1)
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--band", type=int, default=0)
+    ap.add_argument("--mode", default="stream")
     ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
     f = Filter.parse(a.filter)
     g = TileGrid.create(a.height, a.width, a.channels, a.workers)
-    vc = VirtualCluster(g, f, halo_depth=a.k or None, band=a.band or None)
+    vc = VirtualCluster(g, f, halo_depth=a.k or None, band=a.band or None, mode=a.mode)
     vc.synth(1)
-    plan = vc.rt.plan(a.loops)
+    plan = vc.rt.resident_plan(a.loops) if vc.rt.choose_mode(a.loops) == 'resident' else vc.rt.plan(a.loops)
     vc.run(a.loops)
     K.device_sync()
     best = 1e9
@@ -39,11 +40,14 @@ def main():
         e1.record(vc.rt.stream)
         e1.synchronize()
         best = min(best, e0.elapsed_ms(e1))
+    st = vc.collect_status()
     mpx = a.width * a.height * a.loops / (best * 1e-3) / 1e6
     print(json.dumps({"shape": [a.height, a.width, a.channels], "filter": f.name, "path": f.kind_name,
-                      "loops": a.loops, "workers": a.workers, "plan": plan.__dict__,
+                      "loops": a.loops, "workers": a.workers, "mode": vc.rt.choose_mode(a.loops), "plan": plan.__dict__,
                       "ms": round(best, 4), "mpx_s": round(mpx, 1),
-                      "us_per_iter": round(best * 1e3 / a.loops, 3)}))
+                      "us_per_iter": round(best * 1e3 / a.loops, 3),
+                      "wait_max_us": round(st.max_wait_us, 1), "wait_avg_us": round(st.sum_wait_us / max(st.waits, 1), 2),
+                      "waits": st.waits}))
     vc.close()
 
 
