@@ -36,7 +36,8 @@ def _pick_cxx() -> str:
 
 CXX = _pick_cxx()
 
-HOST_SOURCES = ["host/filters.cpp", "host/decomp.cpp", "host/cpu_engine.cpp", "host/rawio.cpp"]
+HOST_SOURCES = ["host/filters.cpp", "host/decomp.cpp", "host/cpu_engine.cpp", "host/rawio.cpp",
+                "host/planner.cpp"]
 HOST_ORACLE = "host/oracle.cpp"  # compiled separately at -O1 with contraction off
 CUDA_SOURCES = ["cuda/runtime.cu", "cuda/stream_kernel.cu", "cuda/resident_kernel.cu",
                 "cuda/pack_kernels.cu"]
@@ -117,7 +118,7 @@ def build_native(force: bool = False) -> Path | None:
     build_cuda(force)
     if not force and not _stale(NATIVE_BIN, [main, HOST_LIB, CUDA_LIB]):
         return NATIVE_BIN
-    _run([CXX, "-std=c++17", "-O2", str(main), "-o", str(NATIVE_BIN), f"-L{LIB}",
+    _run([CXX, "-std=c++17", "-O2", f"-I{CSRC}", str(main), "-o", str(NATIVE_BIN), f"-L{LIB}",
           "-lpconv_host", "-lpconv_cuda", "-Wl,-rpath,$ORIGIN", "-fopenmp"])
     return NATIVE_BIN
 

@@ -28,6 +28,25 @@ int pconv_choose_grid(int64_t rows, int64_t cols, int workers, int* row_div, int
 // Balanced 1-D split with remainder: part idx of `parts` over [0, extent).
 void pconv_split(int64_t extent, int parts, int idx, int64_t* start, int64_t* size);
 
+// ---- launch planner for the GPU kernels (csrc/host/planner.cpp) ------------------------------
+typedef struct pconv_plan_request {
+    int64_t tile_rows, tile_cb;     // largest tile of the grid: rows, bytes per row
+    int64_t min_nbr_rows, min_nbr_cols;  // smallest neighbouring tile extent in pixels (0: none)
+    int32_t C, kind, loops, sms;
+    int32_t bands[8];               // band heights R compiled into the CUDA library
+    int32_t nbands;
+    int32_t force_k, force_R;       // 0: planner decides
+    int32_t resident;               // 1: plan the persistent resident kernel (all CTAs co-resident)
+    int32_t peers;                  // 1: neighbours sit on other GPUs (dearer exchanges)
+    int32_t pad_;
+} pconv_plan_request_t;
+typedef struct pconv_plan {
+    int32_t k, R, TH, TWB, HB, ntx, nty, waves;
+    double est_us;                  // modelled time per launch (stream) / per run (resident)
+} pconv_plan_t;
+// 0: ok, 1: no feasible plan, <0: bad request.
+int pconv_plan(const pconv_plan_request_t* req, pconv_plan_t* out);
+
 // ---- oracle: whole image, zero padded, scalar, deliberately naive ----------------------------
 // src/dst: H x (W*C) bytes, dense. Applies the filter `loops` times; result is in dst.
 // scratch must hold H*W*C bytes (ping-pong partner). Returns 0.

@@ -1,0 +1,86 @@
+// Launch planner (native): region geometry and temporal-blocking depth for the sm_100a kernels.
+//
+// A CTA region is RH = 16*R rows x 512 bytes held in registers (R = band height per warp), of which
+// the interior TH x TWB (TH <= RH - 2k, TWB = 512 - 2*HB, HB = roundup16(k*C)) is written back
+// after k fused iterations. Deeper k divides the number of launches / cross-GPU synchronisations
+// by k (every BASELINE config is latency- or ALU-bound, never link-bound: SURVEY.md §7.2) but
+// recomputes a thicker halo; the planner minimises a simple time model over (k, R, TH) including
+// the wave quantisation over the SMs. The reference has no scheduler at all: one launch / one MPI
+// exchange per iteration, block size hard-coded to 16 (cuda/cuda_convolute.cu:64).
+//
+// The plan must be identical on every rank, so it only depends on quantities every rank knows.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+
+#include "pconv_host.h"
+
+namespace {
+
+constexpr int kRegionBytes = 512, kWarps = 16;
+// Modelled SM throughput in region bytes per clock (B200 measurements, profiles/): only used to
+// rank candidate plans, never reported as a result.
+double bytes_per_clk(int kind) {
+    return kind == PCONV_KIND_SEP121 ? 20.0 : (kind == PCONV_KIND_INT ? 9.0 : 4.0);
+}
+constexpr double kClockGHz = 1.8, kLaunchUs = 4.0, kLoadBytesPerUsPerSm = 40e3;
+constexpr double kExchangeUs = 3.0, kExchangeUsPeer = 6.0;
+
+int roundup(int v, int m) { return (v + m - 1) / m * m; }
+int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+extern "C" int pconv_plan(const pconv_plan_request_t* q, pconv_plan_t* out) {
+    if (!q || !out || q->nbands < 1 || q->tile_rows < 1 || q->tile_cb < 1 || q->C < 1) return -1;
+    const int loops = std::max(q->loops, 1);
+    const int sms = q->sms > 0 ? q->sms : 148;
+    const double rate = bytes_per_clk(q->kind) * kClockGHz * 1e3;  // region bytes per us per SM
+    int max_band = 0;
+    for (int i = 0; i < q->nbands; ++i) max_band = std::max(max_band, q->bands[i]);
+    int kmax = std::min({loops, (kWarps * max_band - 1) / 2, (kRegionBytes / 2 - 64) / q->C});
+    if (q->min_nbr_rows > 0) kmax = std::min<int64_t>(kmax, q->min_nbr_rows);
+    if (q->min_nbr_cols > 0) kmax = std::min<int64_t>(kmax, q->min_nbr_cols);
+    kmax = std::max(kmax, 1);
+    const int k_lo = q->force_k > 0 ? q->force_k : 1, k_hi = q->force_k > 0 ? q->force_k : kmax;
+    const double t_x = q->peers ? kExchangeUsPeer : kExchangeUs;
+    bool found = false;
+    double best = 0.0;
+    for (int k = k_lo; k <= k_hi; ++k) {
+        const int HB = roundup(std::max(k * q->C, 1), 16), TWB = kRegionBytes - 2 * HB;
+        if (TWB < std::max(64, q->resident ? HB : 0)) continue;
+        const int64_t ntx = ceil_div(q->tile_cb, TWB);
+        for (int bi = 0; bi < q->nbands; ++bi) {
+            const int R = q->bands[bi];
+            if (q->force_R > 0 && R != q->force_R) continue;
+            const int RH = kWarps * R, th_max = RH - 2 * k;
+            if (th_max < (q->resident ? k : 1)) continue;
+            const int64_t nty = ceil_div(q->tile_rows, th_max);
+            if (q->resident && ntx * nty > sms) continue;   // every CTA must be co-resident
+            int TH = (int)ceil_div(q->tile_rows, nty);      // balance rows over the same tile count
+            if (q->resident) TH = std::max(TH, k);
+            const int64_t waves = ceil_div(ntx * nty, sms);
+            double total, per_launch;
+            if (q->resident) {
+                const int64_t nblocks = ceil_div(loops, k);
+                total = kLaunchUs + (RH * (double)kRegionBytes + (double)TH * TWB) / kLoadBytesPerUsPerSm +
+                        nblocks * (k * RH * (double)kRegionBytes / rate) + (nblocks - 1) * t_x;
+                per_launch = total;
+            } else {
+                const double t_tile = RH * (double)kRegionBytes / kLoadBytesPerUsPerSm +
+                                      k * RH * (double)kRegionBytes / rate +
+                                      (double)TH * TWB / kLoadBytesPerUsPerSm;
+                per_launch = kLaunchUs + waves * t_tile;
+                total = ceil_div(loops, k) * per_launch;
+            }
+            if (!found || total < best - 1e-9) {
+                found = true;
+                best = total;
+                out->k = k; out->R = R; out->TH = TH; out->TWB = TWB; out->HB = HB;
+                out->ntx = (int32_t)ntx; out->nty = (int32_t)nty; out->waves = (int32_t)waves;
+                out->est_us = per_launch;
+            }
+        }
+    }
+    return found ? 0 : 1;   // 1: no feasible plan (resident: the tile does not fit on chip)
+}

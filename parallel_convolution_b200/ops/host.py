@@ -31,6 +31,20 @@ class FilterSpec(C.Structure):
         return np.array(list(self.w), dtype=np.int32).reshape(3, 3)
 
 
+class PlanRequest(C.Structure):
+    _fields_ = [("tile_rows", C.c_int64), ("tile_cb", C.c_int64), ("min_nbr_rows", C.c_int64),
+                ("min_nbr_cols", C.c_int64), ("C", C.c_int32), ("kind", C.c_int32),
+                ("loops", C.c_int32), ("sms", C.c_int32), ("bands", C.c_int32 * 8),
+                ("nbands", C.c_int32), ("force_k", C.c_int32), ("force_R", C.c_int32),
+                ("resident", C.c_int32), ("peers", C.c_int32), ("pad_", C.c_int32)]
+
+
+class PlanResult(C.Structure):
+    _fields_ = [("k", C.c_int32), ("R", C.c_int32), ("TH", C.c_int32), ("TWB", C.c_int32),
+                ("HB", C.c_int32), ("ntx", C.c_int32), ("nty", C.c_int32), ("waves", C.c_int32),
+                ("est_us", C.c_double)]
+
+
 @lru_cache(maxsize=1)
 def lib() -> C.CDLL:
     path = _build.ensure_host()
@@ -54,6 +68,7 @@ def lib() -> C.CDLL:
     L.pconv_synth_rect.argtypes = [C.c_uint64, i64, i64, i64, i64, i64, u8p, i64]
     L.pconv_synth_rect.restype = None
     L.pconv_host_version.restype = C.c_char_p
+    L.pconv_plan.argtypes = [C.POINTER(PlanRequest), C.POINTER(PlanResult)]
     return L
 
 
@@ -94,6 +109,25 @@ def split(extent: int, parts: int, idx: int) -> tuple[int, int]:
     s, n = C.c_int64(), C.c_int64()
     lib().pconv_split(extent, parts, idx, C.byref(s), C.byref(n))
     return s.value, n.value
+
+
+def plan(tile_rows: int, tile_cb: int, Cn: int, kind: int, loops: int, bands: list[int], *,
+         min_nbr_rows: int = 0, min_nbr_cols: int = 0, sms: int = 148, force_k: int = 0,
+         force_R: int = 0, resident: bool = False, peers: bool = False) -> PlanResult | None:
+    """Native launch planner (csrc/host/planner.cpp). None when no plan is feasible."""
+    q = PlanRequest()
+    q.tile_rows, q.tile_cb, q.min_nbr_rows, q.min_nbr_cols = tile_rows, tile_cb, min_nbr_rows, min_nbr_cols
+    q.C, q.kind, q.loops, q.sms = Cn, kind, loops, sms
+    for i, b in enumerate(bands[:8]):
+        q.bands[i] = b
+    q.nbands = min(len(bands), 8)
+    q.force_k, q.force_R = force_k or 0, force_R or 0
+    q.resident, q.peers = int(resident), int(peers)
+    out = PlanResult()
+    rc = lib().pconv_plan(C.byref(q), C.byref(out))
+    if rc < 0:
+        raise ValueError("bad plan request")
+    return out if rc == 0 else None
 
 
 def oracle(image: np.ndarray, f: FilterSpec, loops: int) -> np.ndarray:

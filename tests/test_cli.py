@@ -1,0 +1,78 @@
+"""CLI parity with the reference programs (argument grammar, blur_ output, printed seconds) and the
+extras: --json, --synthetic, --verify, checkpoint/resume, error handling. CPU only."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from parallel_convolution_b200.models.filters import Filter
+from parallel_convolution_b200.ops import host
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_cli(*args, cwd=None):
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    return subprocess.run([sys.executable, "-m", "parallel_convolution_b200", *map(str, args)],
+                          capture_output=True, text=True, cwd=cwd or ROOT, env=env, timeout=180)
+
+
+@pytest.fixture()
+def raw(tmp_path):
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, (40, 56), dtype=np.uint8)
+    p = tmp_path / "pic_56_40.raw"
+    img.tofile(p)
+    return p, img
+
+
+def test_reference_grammar_and_blur_prefix(raw):
+    p, img = raw
+    r = run_cli(p, 56, 40, 7, "grey", "--backend", "cpu")
+    assert r.returncode == 0, r.stderr
+    assert float(r.stdout.strip()) >= 0.0
+    out = p.parent / ("blur_" + p.name)          # prefix on the BASENAME (reference defect D8 fixed)
+    got = np.fromfile(out, dtype=np.uint8).reshape(40, 56)
+    assert np.array_equal(got, host.oracle(img, Filter.builtin("gaussian").spec, 7))
+
+
+def test_usage_error_exit_code(raw):
+    p, _ = raw
+    r = run_cli(p, 56, 40, 7)                    # missing rgb/grey
+    assert r.returncode != 0 and "image_name width height loops [rgb/grey]" in r.stderr
+    r = run_cli(p, 56, 40, 7, "purple")
+    assert r.returncode != 0
+
+
+def test_short_file_fails_fast(raw):
+    p, _ = raw
+    r = run_cli(p, 560, 400, 1, "grey", "--backend", "cpu")
+    assert r.returncode == 1 and "need" in r.stderr
+
+
+def test_json_synthetic_verify_filter(tmp_path):
+    r = run_cli("synthetic.raw", 37, 29, 4, "rgb", "--backend", "cpu", "--synthetic", 3, "--json",
+                "--filter", "0,-1,0,-1,5,-1,0,-1,0", "--verify", "-o", tmp_path / "o.raw")
+    assert r.returncode == 0, r.stderr
+    rep = json.loads(r.stdout)
+    assert rep["verified"] is True and rep["filter"]["path"] == "int-swar" and rep["iterations"] == 4
+    assert os.path.getsize(tmp_path / "o.raw") == 37 * 29 * 3
+
+
+def test_checkpoint_and_resume_are_bit_identical(raw, tmp_path):
+    p, img = raw
+    full = tmp_path / "full.raw"
+    assert run_cli(p, 56, 40, 10, "grey", "--backend", "cpu", "-o", full).returncode == 0
+    part = tmp_path / "part.raw"
+    # run 10 iterations with a checkpoint every 4, then pretend the job died after the second one
+    r = run_cli(p, 56, 40, 10, "grey", "--backend", "cpu", "-o", part, "--checkpoint-every", 4, "--no-output")
+    assert r.returncode == 0, r.stderr
+    side = json.loads(open(str(part) + ".ckpt.json").read())
+    assert side["iterations_done"] == 8
+    r = run_cli(p, 56, 40, 10, "grey", "--backend", "cpu", "-o", part, "--resume")
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.fromfile(part, dtype=np.uint8), np.fromfile(full, dtype=np.uint8))
+    assert not os.path.exists(str(part) + ".ckpt.json")    # cleaned up after a complete run
