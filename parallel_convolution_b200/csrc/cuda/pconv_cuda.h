@@ -35,7 +35,8 @@ typedef struct pconv_sync {
     uint32_t signal_value;      // last CTA stores this to every remote flag (0: no signal)
     uint64_t timeout_ns;        // watchdog for the spin (0: default 10 s)
     uint64_t* status;           // [0] error code (1 = watchdog fired), [1] max wait ns, [2] sum wait
-                                // ns, [3] number of waits
+                                // ns, [3] number of waits; resident kernel probe CTA: [4] publish ns,
+                                // [5] flag+wait ns, [6] halo reload ns, [7] compute ns, [8] exchanges
     int32_t inject_delay_ns;    // fault injection: delay my signal by this much (tests)
     int32_t inject_drop_signal; // fault injection: never signal (the peer's watchdog must fire)
 } pconv_sync_t;

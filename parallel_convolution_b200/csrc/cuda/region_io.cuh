@@ -72,33 +72,46 @@ __device__ __forceinline__ uint4 load_chunk(const pconv_geometry_t& g, const Sou
 // Load R consecutive rows of one 16-byte column strip (a warp's band) into registers. The column
 // classification (owner, offset, fast/slow) is done once; per row only the owning tile-row is
 // selected, so the common case costs a compare, a 64-bit multiply-add and one 128-bit load.
-template <int R>
+template <int R, bool MASKED = false>
 __device__ __forceinline__ void load_band(uint4 (&rows)[R], const pconv_geometry_t& g,
-                                          const SourceSet& s, int64_t gr0, int64_t gb) {
+                                          const SourceSet& s, int64_t gr0, int64_t gb,
+                                          uint32_t mask = 0xffffffffu) {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     const bool col_out = gb + 16 <= 0 || gb >= g.img_cb;
     const bool col_whole = gb >= 0 && gb + 16 <= g.img_cb;
     const int oc = owner_of(gb < 0 ? 0 : gb, g.cb_lo);
-    const bool fast = col_whole && owner_of(gb + 15, g.cb_lo) == oc;
-    // per owning tile-row: pointer to (image row 0 of that tile, my column) and its pitch
-    const uint8_t* bp[3];
-    int64_t pp[3];
-#pragma unroll
-    for (int o = 0; o < 3; ++o) {
-        const int d = o * 3 + oc;
-        pp[o] = s.pitch[d];
-        bp[o] = s.p[d] ? s.p[d] + (gb - g.cb_lo[oc]) - g.row_lo[o] * pp[o] : nullptr;
-    }
+    const bool one_owner = col_whole && owner_of(gb + 15, g.cb_lo) == oc;
+    // Per owning tile-row (scalars, never indexed dynamically -> they stay in registers): pointer to
+    // (image row 0 of that tile, my column), its pitch, and whether 128-bit loads are legal there.
+    const int64_t p0 = s.pitch[oc], p1 = s.pitch[3 + oc], p2 = s.pitch[6 + oc];
+    const int64_t cofs = gb - g.cb_lo[oc];
+    const uint8_t* b0 = s.p[oc] ? s.p[oc] + cofs - g.row_lo[0] * p0 : nullptr;
+    const uint8_t* b1 = s.p[3 + oc] ? s.p[3 + oc] + cofs - g.row_lo[1] * p1 : nullptr;
+    const uint8_t* b2 = s.p[6 + oc] ? s.p[6 + oc] + cofs - g.row_lo[2] * p2 : nullptr;
+    const bool f0 = one_owner && b0 && ((reinterpret_cast<uintptr_t>(b0) | (uintptr_t)p0) & 15u) == 0;
+    const bool f1 = one_owner && b1 && ((reinterpret_cast<uintptr_t>(b1) | (uintptr_t)p1) & 15u) == 0;
+    const bool f2 = one_owner && b2 && ((reinterpret_cast<uintptr_t>(b2) | (uintptr_t)p2) & 15u) == 0;
+    uint32_t slow = 0;   // rows that need the byte-wise path (rare: odd tile widths, image edge)
 #pragma unroll
     for (int i = 0; i < R; ++i) {
+        if (MASKED && !((mask >> i) & 1u)) continue;   // keep this row (resident halo refresh)
         const int64_t gr = gr0 + i;
         if (col_out || gr < 0 || gr >= g.img_rows) { rows[i] = z; continue; }
-        const int o = owner_of(gr, g.row_lo);
-        const uint8_t* a = bp[o] + gr * pp[o];
-        if (fast && bp[o] != nullptr && (reinterpret_cast<uintptr_t>(a) & 15u) == 0)
-            rows[i] = __ldcg(reinterpret_cast<const uint4*>(a));
-        else
+        const bool in0 = gr < g.row_lo[1], in1 = gr < g.row_lo[2];
+        const uint8_t* base = in0 ? b0 : (in1 ? b1 : b2);
+        const int64_t pitch = in0 ? p0 : (in1 ? p1 : p2);
+        const bool fast = in0 ? f0 : (in1 ? f1 : f2);
+        if (fast) rows[i] = __ldcg(reinterpret_cast<const uint4*>(base + gr * pitch));
+        else slow |= 1u << i;
+    }
+    if (slow) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            if (!((slow >> i) & 1u)) continue;
+            const int64_t gr = gr0 + i;
+            const int o = owner_of(gr, g.row_lo);
             rows[i] = load_chunk_bytes(g, s, o, gr - g.row_lo[o], gb);
+        }
     }
 }
 
@@ -115,6 +128,28 @@ __device__ __forceinline__ void store_chunk(uint8_t* __restrict__ dst, const pco
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         for (int t = 0; t < 16; ++t)
             if (lb + t >= 0 && lb + t < tile_cb) a[t] = (uint8_t)(w[t >> 2] >> (8 * (t & 3)));
+    }
+}
+
+// Store the rows of a band selected by `mask` (bit i = row i) into my tile; the column test and the
+// address arithmetic are hoisted out of the row loop.
+template <int R>
+__device__ __forceinline__ void store_band(const uint4 (&rows)[R], uint32_t mask,
+                                           uint8_t* __restrict__ dst, const pconv_geometry_t& g,
+                                           int64_t gr0, int64_t gb) {
+    const int64_t lb = gb - g.cb_lo[1], lr0 = gr0 - g.row_lo[1];
+    const int64_t tile_rows = g.row_lo[2] - g.row_lo[1], tile_cb = g.cb_lo[2] - g.cb_lo[1];
+    if (mask == 0u || lb + 16 <= 0 || lb >= tile_cb) return;
+    uint8_t* a0 = dst + lr0 * g.pitch + lb;
+    const bool fast = lb >= 0 && lb + 16 <= tile_cb && (reinterpret_cast<uintptr_t>(a0) & 15u) == 0 &&
+                      (g.pitch & 15) == 0;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        if (!((mask >> i) & 1u)) continue;
+        const int64_t lr = lr0 + i;
+        if (lr < 0 || lr >= tile_rows) continue;
+        if (fast) __stcg(reinterpret_cast<uint4*>(a0 + i * g.pitch), rows[i]);
+        else store_chunk(dst, g, gr0 + i, gb, rows[i]);
     }
 }
 

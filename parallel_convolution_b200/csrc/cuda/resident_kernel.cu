@@ -90,8 +90,35 @@ resident_kernel(const __grid_constant__ ResidentArgs A) {
     // image) — and is refreshed at each exchange so that staleness never travels more than k pixels.
     const int vr = (int)min((int64_t)A.TH, g.row_lo[2] - g.row_lo[1] - (int64_t)ti * A.TH);   // valid rows
     const int vcb = (int)min((int64_t)A.TWB, g.cb_lo[2] - g.cb_lo[1] - (int64_t)tj * A.TWB);  // valid bytes
-    const bool col_int = (16 * lane >= A.HB) && (16 * lane < A.HB + vcb);
+    const bool col_int = (16 * lane >= A.HB) && (16 * lane < A.HB + vcb);        // overlaps my interior
+    const bool col_full = (16 * lane >= A.HB) && (16 * lane + 16 <= A.HB + vcb); // entirely my interior
     const bool col_edge = col_int && (16 * lane < 2 * A.HB || 16 * lane + 16 > vcb);
+    // Row masks of this thread's band (bit i = band row i), fixed for the whole run:
+    //   m_publish : rows/chunks whose current value the eight neighbours' halos will read
+    //   m_reload  : everything that is not entirely mine (a chunk straddling the tile edge holds
+    //               some neighbour bytes: it is re-read whole — my own bytes come back from the strip
+    //               I just published)
+    //   m_final   : my interior
+    uint32_t m_publish = 0, m_reload = 0, m_final = 0;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int rr = warp * R + i;
+        const bool row_int = rr >= k && rr < k + vr;
+        const bool row_edge = rr < 2 * k || rr >= vr;
+        if (row_int && col_int && (row_edge || col_edge)) m_publish |= 1u << i;
+        if (!(row_int && col_full)) m_reload |= 1u << i;
+        if (row_int && col_int) m_final |= 1u << i;
+    }
+
+    // Phase probe: one interior CTA accumulates where its time goes (publish / flag+wait / reload /
+    // compute) into status[4..8] — the "exposed halo-exchange time" of the run, measured on the
+    // device with %globaltimer.
+    const bool probe = A.sync.status != nullptr && threadIdx.x == 0 &&
+                       blockIdx.x == (unsigned)((A.nty / 2) * A.ntx + A.ntx / 2);
+    uint64_t t_pub = 0, t_wait = 0, t_load = 0, t_comp = 0, t_mark = probe ? globaltimer_ns() : 0;
+    auto lap = [&](uint64_t& acc) {
+        if (probe) { const uint64_t t = globaltimer_ns(); acc += t - t_mark; t_mark = t; }
+    };
 
     const int nblocks = (A.loops + k - 1) / k;
     for (int b = 0; b < nblocks; ++b) {
@@ -99,14 +126,9 @@ resident_kernel(const __grid_constant__ ResidentArgs A) {
             const int par = b & 1;
             uint8_t* mine = A.self[par];
             // 1. publish the border strips of my interior (what the eight neighbours' halos read)
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const int rr = warp * R + i;
-                const bool row_int = rr >= k && rr < k + vr;
-                const bool row_edge = rr < 2 * k || rr >= vr;
-                if (row_int && col_int && (row_edge || col_edge)) store_chunk(mine, g, grw + i, gb, rows[i]);
-            }
+            store_band<R>(rows, m_publish, mine, g, grw, gb);
             __syncthreads();
+            lap(t_pub);
             // 2. announce epoch b: own flag + mirrored ring entries on neighbouring GPUs
             const uint32_t epoch = A.epoch_base + (uint32_t)b;
             if (threadIdx.x == 0) {   // local consumers: gpu scope is enough (and much cheaper)
@@ -138,29 +160,30 @@ resident_kernel(const __grid_constant__ ResidentArgs A) {
                 }
             }
             __syncthreads();
+            lap(t_wait);
             // 4. re-load my halo (whole rows above/below the interior, edge chunks of interior rows)
-            const SourceSet& P = A.src[par];
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-                const int rr = warp * R + i;
-                const bool row_int = rr >= k && rr < k + vr;
-                if (!row_int || !col_int) rows[i] = load_chunk(g, P, grw + i, gb);
-            }
+            if (m_reload) load_band<R, true>(rows, g, A.src[par], grw, gb, m_reload);
+            if (probe) { asm volatile("" ::"r"(rows[0].x), "r"(rows[R - 1].x)); }
+            lap(t_load);
         }
         // 5. iterate
         const int kb = min(k, A.loops - b * k);
         if (masked) region_iterate<KIND, C, R, true>(rows, eb, kb, cmask, rowmask, A.f);
         else region_iterate<KIND, C, R, false>(rows, eb, kb, cmask, rowmask, A.f);
         __syncthreads();  // edge buffers: next block restarts at parity 0
+        lap(t_comp);
+    }
+    if (probe) {
+        unsigned long long* st = reinterpret_cast<unsigned long long*>(A.sync.status);
+        atomicAdd(st + 4, (unsigned long long)t_pub);
+        atomicAdd(st + 5, (unsigned long long)t_wait);
+        atomicAdd(st + 6, (unsigned long long)t_load);
+        atomicAdd(st + 7, (unsigned long long)t_comp);
+        atomicAdd(st + 8, (unsigned long long)(nblocks - 1));
     }
 
     // ---- final interior -> the parity without live strips -------------------------------------------
-    uint8_t* dst = A.self[nblocks & 1];
-#pragma unroll
-    for (int i = 0; i < R; ++i) {
-        const int rr = warp * R + i;
-        if (col_int && rr >= k && rr < k + vr) store_chunk(dst, g, grw + i, gb, rows[i]);
-    }
+    store_band<R>(rows, m_final, A.self[nblocks & 1], g, grw, gb);
     if (threadIdx.x == 0 && s_wait_ns) record_wait(A.sync.status, s_wait_ns);
 
     // ---- launch-level protocol: publish "run done" -------------------------------------------------

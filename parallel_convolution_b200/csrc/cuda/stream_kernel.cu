@@ -99,11 +99,13 @@ stream_kernel(const __grid_constant__ StreamArgs A) {
 
         // ---- store the interior straight from registers ------------------------------------------
         const bool col_in = (16 * lane >= A.HB) && (16 * lane < A.HB + A.TWB);
+        uint32_t m_store = 0;
 #pragma unroll
         for (int i = 0; i < R; ++i) {
             const int rr = warp * R + i;
-            if (col_in && rr >= k && rr < k + A.TH) store_chunk(A.dst, g, grw + i, gb, rows[i]);
+            if (col_in && rr >= k && rr < k + A.TH) m_store |= 1u << i;
         }
+        store_band<R>(rows, m_store, A.dst, g, grw, gb);
         __syncthreads();  // edge buffers are reused by the next tile
     }
 

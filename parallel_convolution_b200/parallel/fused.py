@@ -26,10 +26,10 @@ from .decomposition import TileGrid
 from .plan import StreamPlan, plan_stream
 
 FLAG_BYTES = 256      # 9 x u32 flags + padding
-STATUS_WORDS = 4      # u64: error, max wait ns, sum wait ns, waits
+STATUS_WORDS = 9      # u64: error, max wait ns, sum wait ns, waits, probe: publish/wait/reload/compute ns, exchanges
 CTA_FLAG_BYTES = 4096  # resident kernel: (nty+2)*(ntx+2) u32 epochs, nty*ntx <= #SMs
 # control block layout (one cudaMalloc, one IPC handle): flags | counter | status | cta_flags
-OFF_COUNTER, OFF_STATUS, OFF_CTA = FLAG_BYTES, FLAG_BYTES + 64, FLAG_BYTES + 128
+OFF_COUNTER, OFF_STATUS, OFF_CTA = FLAG_BYTES, FLAG_BYTES + 64, FLAG_BYTES + 64 + 128
 CTL_BYTES = OFF_CTA + CTA_FLAG_BYTES
 
 
@@ -204,6 +204,9 @@ class TileDriver:
         out = np.zeros(STATUS_WORDS, dtype=np.uint64)
         K.memcpy_async(out.ctypes.data, self.mem.status, 8 * STATUS_WORDS, K.D2H, self.stream)
         K.stream_sync(self.stream)
+        self.probe = {"publish_us": float(out[4]) / 1e3, "wait_us": float(out[5]) / 1e3,
+                      "reload_us": float(out[6]) / 1e3, "compute_us": float(out[7]) / 1e3,
+                      "exchanges": int(out[8])}
         return bool(out[0]), float(out[1]) / 1e3, float(out[2]) / 1e3, int(out[3])
 
 

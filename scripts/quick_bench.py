@@ -47,7 +47,7 @@ def main():
                       "ms": round(best, 4), "mpx_s": round(mpx, 1),
                       "us_per_iter": round(best * 1e3 / a.loops, 3),
                       "wait_max_us": round(st.max_wait_us, 1), "wait_avg_us": round(st.sum_wait_us / max(st.waits, 1), 2),
-                      "waits": st.waits}))
+                      "waits": st.waits, "probe": getattr(list(vc.rt.drivers.values())[0], "probe", None)}))
     vc.close()
 
 
