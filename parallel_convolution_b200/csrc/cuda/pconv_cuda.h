@@ -64,8 +64,11 @@ int pconv_stream_launch(const pconv_stream_params_t* p, void* stream);
 // `pp` holds 2*nranks parameter blocks, [2*r + 0] reading buffer parity A and [2*r + 1] parity B of
 // (virtual) rank r; launch i uses block (i & 1) with k = ks[i]; with use_flags the epochs are
 // signal = epoch0 + i + 1 and wait = (i ? epoch0 + i : first_wait).
+// first_flags (optional, [nranks]): flag array the FIRST launch waits on instead of
+// sync.local_flags — the "input ready" bank of the pipelined step protocol.
 int pconv_stream_run(const pconv_stream_params_t* pp, int nranks, const int32_t* ks, int nlaunch,
-                     uint32_t epoch0, int use_flags, uint32_t first_wait, void* stream);
+                     uint32_t epoch0, int use_flags, uint32_t first_wait, uint32_t* const* first_flags,
+                     void* stream);
 // Stand-alone halo-protocol step (1 CTA): wait until every existing neighbour reached wait_value,
 // then announce signal_value to them. Brackets host/device copies into a tile buffer between runs
 // so that back-to-back steps need no host barrier (bench.py, streaming ingest).

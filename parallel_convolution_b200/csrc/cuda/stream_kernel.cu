@@ -238,7 +238,7 @@ extern "C" int pconv_stream_launch(const pconv_stream_params_t* p, void* stream)
 
 extern "C" int pconv_stream_run(const pconv_stream_params_t* pp, int nranks, const int32_t* ks,
                                 int nlaunch, uint32_t epoch0, int use_flags, uint32_t first_wait,
-                                void* stream) {
+                                uint32_t* const* first_flags, void* stream) {
     if (!pp || !ks || nranks < 1 || nlaunch < 0) return pconv_rt::fail("bad run arguments");
     for (int i = 0; i < nlaunch; ++i) {
         for (int r = 0; r < nranks; ++r) {
@@ -247,6 +247,7 @@ extern "C" int pconv_stream_run(const pconv_stream_params_t* pp, int nranks, con
             if (use_flags) {
                 p.sync.signal_value = epoch0 + (uint32_t)i + 1u;
                 p.sync.wait_value = i ? epoch0 + (uint32_t)i : first_wait;
+                if (i == 0 && first_wait && first_flags && first_flags[r]) p.sync.local_flags = first_flags[r];
             } else {
                 p.sync.signal_value = p.sync.wait_value = 0u;
             }

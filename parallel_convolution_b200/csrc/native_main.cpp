@@ -125,7 +125,7 @@ int main(int argc, char** argv) {
         std::vector<int32_t> ks;
         for (int done = 0; done < loops; done += plan.k) ks.push_back(std::min(plan.k, loops - done));
         CK(pconv_cuda_event_record(e0, stream));
-        if (!ks.empty()) CK(pconv_stream_run(pp, 1, ks.data(), (int)ks.size(), 0, 0, 0, stream));
+        if (!ks.empty()) CK(pconv_stream_run(pp, 1, ks.data(), (int)ks.size(), 0, 0, 0, nullptr, stream));
         CK(pconv_cuda_event_record(e1, stream));
         void* final_buf = (ks.size() & 1) ? bufB : bufA;   // parity-correct for any loops (defect D4)
         CK(pconv_cuda_memcpy2d_async(result.data(), rb, final_buf, pitch, rb, H, 2, stream));

@@ -44,6 +44,7 @@ class EngineConfig:
     threads: int = 0                 # cpu backend: OpenMP threads per rank
     device: int | None = None        # CUDA device index (default: LOCAL_RANK or 0)
     timeout_ms: float = 10_000.0     # in-kernel watchdog for neighbour flags
+    slots: int = 1                   # buffer sets for pipelined streaming steps (H2D || iterate || D2H)
 
 
 @dataclass
@@ -126,7 +127,7 @@ class ConvEngine:
             from .parallel.fused_runtime import FusedRuntime
             self._impl = FusedRuntime(self.grid, self.filter, self.rank, self.world, self.dist,
                                       halo_depth=cfg.halo_depth, mode=cfg.mode,
-                                      timeout_ms=cfg.timeout_ms)
+                                      timeout_ms=cfg.timeout_ms, slots=cfg.slots)
         else:
             from .parallel.nccl_backend import NcclRuntime
             self._impl = NcclRuntime(self.grid, self.filter, self.rank, self.world, self.dist,
@@ -284,10 +285,15 @@ class ConvEngine:
         for r in rt.local_ranks:
             K.memcpy_async(rt.mems[r].bufs[0], self._pool[index % len(self._pool)][r],
                            rt.mems[r].nbytes - 256, K.D2D, rt.stream)
-        rt.parity = 0
+        rt.parity, rt.slot = 0, 0
         n += rt.end_input()
         _, launches = rt.enqueue(loops)
         return n + launches
+
+    def enqueue_step_pipelined(self, host_in: dict, host_out: dict, loops: int) -> int:
+        """Like ``enqueue_step_pinned`` but on rotating buffer slots and three streams, so the host
+        copies of neighbouring steps overlap the iterations (needs ``slots >= 2``)."""
+        return self._impl.enqueue_step_pipelined(host_in, host_out, loops)
 
     def pinned_buffers(self) -> tuple[dict, dict]:
         """Pinned host staging (input, output) per local tile, dense rows x tile_bytes."""
@@ -313,18 +319,21 @@ class ConvEngine:
             a = host_in[r]
             K.memcpy2d_async(rt.mems[r].bufs[0], rt.pitch, a.ctypes.data, a.shape[1], a.shape[1],
                              a.shape[0], K.H2D, rt.stream)
-        rt.parity = 0
+        rt.parity, rt.slot = 0, 0
         n += rt.end_input()
         _, launches = rt.enqueue(loops)
         for r in rt.local_ranks:
             o = host_out[r]
-            K.memcpy2d_async(o.ctypes.data, o.shape[1], rt.mems[r].bufs[rt.parity], rt.pitch,
+            K.memcpy2d_async(o.ctypes.data, o.shape[1], rt.mems[r].bufs[2 * rt.slot + rt.parity], rt.pitch,
                              o.shape[1], o.shape[0], K.D2H, rt.stream)
         return n + launches
 
     def synchronize(self) -> None:
         from .ops import cuda as K
-        K.stream_sync(self._impl.stream)
+        if hasattr(self._impl, "pipeline_sync"):
+            self._impl.pipeline_sync()
+        else:
+            K.stream_sync(self._impl.stream)
 
     @property
     def stream(self) -> int:

@@ -58,7 +58,7 @@ def lib() -> C.CDLL:
     vp, i64 = C.c_void_p, C.c_int64
     L.pconv_stream_launch.argtypes = [C.POINTER(StreamParams), vp]
     L.pconv_stream_run.argtypes = [C.POINTER(StreamParams), C.c_int, C.POINTER(C.c_int32), C.c_int,
-                                   C.c_uint32, C.c_int, C.c_uint32, vp]
+                                   C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_void_p), vp]
     L.pconv_sync_launch.argtypes = [C.POINTER(Sync), vp]
     L.pconv_stream_band_heights.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int]
     if hasattr(L, "pconv_resident_launch"):
@@ -269,11 +269,12 @@ def stream_launch(p: StreamParams, stream: int) -> None:
 
 
 def stream_run(blocks, nranks: int, ks: list[int], epoch0: int, use_flags: bool, stream: int,
-               first_wait: int = 0) -> None:
+               first_wait: int = 0, first_flags: list[int] | None = None) -> None:
     """``blocks``: ctypes array of 2*nranks StreamParams (see pconv_stream_run)."""
     arr = (C.c_int32 * len(ks))(*ks)
+    ff = (C.c_void_p * nranks)(*first_flags) if first_flags else None
     _check(lib().pconv_stream_run(blocks, nranks, arr, len(ks), epoch0, 1 if use_flags else 0,
-                                  first_wait, stream), "stream_run")
+                                  first_wait, ff, stream), "stream_run")
 
 
 def sync_launch(s: Sync, stream: int) -> None:

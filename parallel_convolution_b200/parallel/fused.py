@@ -25,7 +25,8 @@ from ..ops import cuda as K
 from .decomposition import TileGrid
 from .plan import StreamPlan, plan_stream
 
-FLAG_BYTES = 256      # 9 x u32 flags + padding
+FLAG_BYTES = 256      # bank 0 (+0): launch epochs, bank 1 (+64): "input ready" step counters
+BANK1 = 64
 STATUS_WORDS = 9      # u64: error, max wait ns, sum wait ns, waits, probe: publish/wait/reload/compute ns, exchanges
 CTA_FLAG_BYTES = 4096  # resident kernel: (nty+2)*(ntx+2) u32 epochs, nty*ntx <= #SMs
 # control block layout (one cudaMalloc, one IPC handle): flags | counter | status | cta_flags
@@ -52,9 +53,11 @@ class RankMemory:
     cta_flags: int = 0
 
     @staticmethod
-    def allocate(rows: int, pitch: int) -> "RankMemory":
+    def allocate(rows: int, pitch: int, slots: int = 1) -> "RankMemory":
+        """``slots`` independent ping-pong buffer pairs (slot s = bufs[2s], bufs[2s+1]) so that the
+        host copies of one step overlap the iterations of another."""
         nbytes = rows * pitch + 256
-        bufs = [K.malloc(nbytes), K.malloc(nbytes)]
+        bufs = [K.malloc(nbytes) for _ in range(2 * slots)]
         ctl = K.malloc(CTL_BYTES)
         return RankMemory(bufs, ctl, ctl + OFF_COUNTER, ctl + OFF_STATUS, nbytes, True, ctl + OFF_CTA)
 
@@ -117,9 +120,10 @@ class TileDriver:
 
     # -- launches ---------------------------------------------------------------------------
     def _params(self, plan: StreamPlan, k: int, src_parity: int, wait: int, signal: int,
-                grid_ctas: int = 0) -> K.StreamParams:
+                grid_ctas: int = 0, slot: int = 0) -> K.StreamParams:
         p = K.StreamParams()
         p.g = self._geom
+        src_parity += 2 * slot
         for d in range(9):
             nb = self.neighbors[d]
             p.src[d] = nb.bufs[src_parity] if nb is not None else None
@@ -139,9 +143,10 @@ class TileDriver:
         return p
 
     def resident_params(self, plan: StreamPlan, loops: int, src_parity: int, wait: int, signal: int,
-                        cta_epoch: int) -> K.ResidentParams:
+                        cta_epoch: int, slot: int = 0, wait_bank1: bool = False) -> K.ResidentParams:
         p = K.ResidentParams()
         p.g = self._geom
+        src_parity += 2 * slot
         for d in range(9):
             nb = self.neighbors[d]
             p.src_a[d] = nb.bufs[src_parity] if nb is not None else None
@@ -155,7 +160,7 @@ class TileDriver:
         p.nty, p.ntx = plan.nty, plan.ntx
         p.cta_flags = self.mem.cta_flags
         p.epoch_base = cta_epoch
-        p.sync.local_flags = self.mem.flags
+        p.sync.local_flags = self.mem.flags + (BANK1 if wait_bank1 else 0)
         p.sync.done_counter = self.mem.counter
         p.sync.status = self.mem.status
         p.sync.wait_value, p.sync.signal_value = wait, signal
@@ -173,6 +178,19 @@ class TileDriver:
         else:
             wait = signal = 0
         K.stream_launch(self._params(plan, k, src_parity, wait, signal), self.stream)
+
+    def sync_params(self, wait: int, signal: int, bank: int = 0) -> K.Sync:
+        """Parameters of a stand-alone protocol step on flag bank 0 (launch epochs) or 1 (inputs)."""
+        s = K.Sync()
+        off = BANK1 if bank else 0
+        s.local_flags = self.mem.flags + off
+        for d in range(9):
+            nb = self.neighbors[d]
+            s.remote_flags[d] = (nb.flags + off + 4 * (8 - d)) if (nb is not None and d != 4) else None
+        s.done_counter, s.status = self.mem.counter, self.mem.status
+        s.wait_value, s.signal_value, s.timeout_ns = wait, signal, self.timeout_ns
+        s.inject_drop_signal = 1 if self.inject_drop_signal else 0
+        return s
 
     # -- data movement ----------------------------------------------------------------------
     def upload(self, tile: np.ndarray, parity: int = 0) -> None:

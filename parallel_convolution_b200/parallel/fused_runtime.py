@@ -26,10 +26,13 @@ from .plan import StreamPlan
 class FusedRuntime:
     def __init__(self, grid: TileGrid, filt: Filter, rank: int, world: int, dist,
                  halo_depth: int | None = None, mode: str = "auto", timeout_ms: float = 10_000.0,
-                 band: int | None = None):
+                 band: int | None = None, slots: int = 1):
         self.grid, self.filt, self.rank, self.world, self.dist = grid, filt, rank, world, dist
         self.halo_depth, self.mode, self.band = halo_depth, mode, band
         self.pitch = tile_pitch(grid)
+        self.slots, self.slot = max(1, int(slots)), 0
+        self._pipe = None
+        self._step = 0
         self.stream = K.stream_create()
         self.sms = K.sm_count()
         self.bands = K.band_heights(filt.kind)
@@ -40,13 +43,13 @@ class FusedRuntime:
                 raise ValueError("one tile per process: grid size must equal the world size")
             from .peer_memory import PeerGroup
             self.local_ranks = [rank]
-            mem = RankMemory.allocate(rows, self.pitch)
+            mem = RankMemory.allocate(rows, self.pitch, self.slots)
             self.mems = {rank: mem}
             self.peers = PeerGroup(rank, world)
             nbrs = {rank: self.peers.exchange(mem, grid.neighbors(rank))}
         else:
             self.local_ranks = list(range(grid.workers))
-            self.mems = {r: RankMemory.allocate(rows, self.pitch) for r in self.local_ranks}
+            self.mems = {r: RankMemory.allocate(rows, self.pitch, self.slots) for r in self.local_ranks}
             nbrs = {r: [self.mems[n] if n >= 0 else None for n in grid.neighbors(r)]
                     for r in self.local_ranks}
         self.drivers = {r: TileDriver(grid, r, filt, self.mems[r], nbrs[r], self.pitch, self.stream,
@@ -63,7 +66,7 @@ class FusedRuntime:
 
     # -- lifecycle ------------------------------------------------------------------------------
     def close(self) -> None:
-        K.stream_sync(self.stream)
+        self.pipeline_sync()
         if self.peers is not None:
             K.device_sync()
             self.peers.barrier()      # nobody may still be reading my buffers
@@ -73,6 +76,9 @@ class FusedRuntime:
         self.mems = {}
         for st in self._rank_streams.values():
             K.stream_destroy(st)
+        if self._pipe is not None:
+            K.stream_destroy(self._pipe["s_in"])
+            K.stream_destroy(self._pipe["s_out"])
         K.stream_destroy(self.stream)
 
     def _barrier(self) -> None:
@@ -85,19 +91,19 @@ class FusedRuntime:
         self._barrier()               # previous run's readers are done with my buffers
         for r, tile in tiles.items():
             self.drivers[r].upload(tile, 0)
-        self.parity = 0
+        self.parity, self.slot = 0, 0
 
     def synth(self, seed: int) -> None:
         self._barrier()
         for d in self.drivers.values():
             d.synth(seed, 0)
-        self.parity = 0
+        self.parity, self.slot = 0, 0
 
     def download(self) -> dict[int, np.ndarray]:
-        return {r: d.download(self.parity) for r, d in self.drivers.items()}
+        return {r: d.download(2 * self.slot + self.parity) for r, d in self.drivers.items()}
 
     def buffer_ptr(self, rank: int, parity: int | None = None) -> int:
-        return self.mems[rank].bufs[self.parity if parity is None else parity]
+        return self.mems[rank].bufs[2 * self.slot + (self.parity if parity is None else parity)]
 
     # -- compute ----------------------------------------------------------------------------------
     def plan(self, loops: int) -> StreamPlan:
@@ -150,8 +156,10 @@ class FusedRuntime:
         nblocks = -(-loops // plan.k)
         first_wait, self._first_wait = getattr(self, "_first_wait", 0), 0
         signal = self.epoch + 1 if self.multi else 0
+        bank1, self._first_bank1 = getattr(self, "_first_bank1", False), False
         params = {r: self.drivers[r].resident_params(plan, loops, self.parity, first_wait if self.multi else 0,
-                                                     signal, self.cta_epoch) for r in self.local_ranks}
+                                                     signal, self.cta_epoch, slot=self.slot,
+                                                     wait_bank1=bank1) for r in self.local_ranks}
         if self._rank_streams:
             fork = K.Event().record(self.stream)
             joins = []
@@ -182,13 +190,75 @@ class FusedRuntime:
         blocks = (K.StreamParams * (2 * n))()
         for i, r in enumerate(self.local_ranks):
             d = self.drivers[r]
-            blocks[2 * i] = d._params(plan, plan.k, self.parity, 0, 0)
-            blocks[2 * i + 1] = d._params(plan, plan.k, self.parity ^ 1, 0, 0)
+            blocks[2 * i] = d._params(plan, plan.k, self.parity, 0, 0, slot=self.slot)
+            blocks[2 * i + 1] = d._params(plan, plan.k, self.parity ^ 1, 0, 0, slot=self.slot)
         first_wait, self._first_wait = getattr(self, "_first_wait", 0), 0
-        K.stream_run(blocks, n, ks, self.epoch, self.multi, self.stream, first_wait)
+        bank1, self._first_bank1 = getattr(self, "_first_bank1", False), False
+        from .fused import BANK1
+        ff = [self.mems[r].flags + BANK1 for r in self.local_ranks] if (bank1 and first_wait) else None
+        K.stream_run(blocks, n, ks, self.epoch, self.multi, self.stream, first_wait, ff)
         self.epoch += len(ks)
         self.parity ^= len(ks) & 1
         return plan, len(ks) * n
+
+    # -- pipelined end-to-end steps: H2D(i+1) || iterate(i) || D2H(i-1) ---------------------------------
+    def _pipeline(self):
+        if self._pipe is None:
+            S = self.slots
+            self._pipe = {"s_in": K.stream_create(), "s_out": K.stream_create(),
+                          "in_done": [K.Event() for _ in range(S)], "comp_done": [K.Event() for _ in range(S)],
+                          "out_done": [K.Event() for _ in range(S)], "used": [False] * S,
+                          "last_epoch": [0] * S}
+        return self._pipe
+
+    def enqueue_step_pipelined(self, host_in: dict, host_out: dict, loops: int) -> int:
+        """One end-to-end step on buffer slot ``step % slots``: pinned host -> device on the copy-in
+        stream, ``loops`` iterations on the compute stream, device -> pinned host on the copy-out
+        stream. Steps on different slots overlap; cross-rank ordering is in-stream (flag bank 1 =
+        "input of step s is in place", bank 0 = launch epochs). ``host_in[r]`` / ``host_out[r]``:
+        pinned 2-D arrays of local tile r (one set per slot is the caller's business)."""
+        P, S = self._pipeline(), self.slots
+        step = self._step
+        slot = step % S
+        self._step += 1
+        n = 0
+        s_in, s_out = P["s_in"], P["s_out"]
+        if P["used"][slot]:
+            K.stream_wait_event(s_in, P["out_done"][slot])          # my previous result left the slot
+            if self.multi and P["last_epoch"][slot]:                # neighbours finished reading it
+                for d in self.drivers.values():
+                    K.sync_launch(d.sync_params(P["last_epoch"][slot], 0, bank=0), s_in)
+                n += len(self.drivers)
+        for r in self.local_ranks:
+            a = host_in[r]
+            K.memcpy2d_async(self.mems[r].bufs[2 * slot], self.pitch, a.ctypes.data, a.shape[1],
+                             a.shape[1], a.shape[0], K.H2D, s_in)
+        if self.multi:
+            for d in self.drivers.values():
+                K.sync_launch(d.sync_params(0, step + 1, bank=1), s_in)
+            n += len(self.drivers)
+        P["in_done"][slot].record(s_in)
+        K.stream_wait_event(self.stream, P["in_done"][slot])
+        self.slot, self.parity = slot, 0
+        if self.multi:
+            self._first_wait, self._first_bank1 = step + 1, True
+        _, launches = self.enqueue(loops)
+        P["last_epoch"][slot] = self.epoch
+        P["used"][slot] = True
+        P["comp_done"][slot].record(self.stream)
+        K.stream_wait_event(s_out, P["comp_done"][slot])
+        for r in self.local_ranks:
+            o = host_out[r]
+            K.memcpy2d_async(o.ctypes.data, o.shape[1], self.mems[r].bufs[2 * slot + self.parity],
+                             self.pitch, o.shape[1], o.shape[0], K.D2H, s_out)
+        P["out_done"][slot].record(s_out)
+        return n + launches
+
+    def pipeline_sync(self) -> None:
+        K.stream_sync(self.stream)
+        if self._pipe is not None:
+            K.stream_sync(self._pipe["s_in"])
+            K.stream_sync(self._pipe["s_out"])
 
     def run(self, loops: int, rep, sync: bool = True) -> None:
         for d in self.drivers.values():

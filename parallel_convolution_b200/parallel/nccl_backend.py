@@ -52,7 +52,7 @@ class NcclRuntime:
                                  [self.mems[self.me] if d == 4 else None for d in range(9)],
                                  self.pitch, self.stream)
         self.drivers = {self.me: self.driver}
-        self.parity = 0
+        self.parity, self.slot = 0, 0
         self.multi = False            # no in-kernel flags on this path
         self._plans: dict[int, StreamPlan] = {}
         self._ghost_key = None
