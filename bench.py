@@ -158,7 +158,9 @@ def run_ours(a) -> dict | None:
     value = px * K_steps / (ms * 1e-3) / 1e6
     e2e = px * K_steps / (ms_e2e * 1e-3) / 1e6
     rep = eng.report
-    plan = eng._impl.plan(LOOPS) if hasattr(eng._impl, "plan") else None
+    impl = eng._impl
+    kmode = impl.choose_mode(LOOPS) if hasattr(impl, "choose_mode") else "stream"
+    plan = impl.resident_plan(LOOPS) if kmode == "resident" else impl.plan(LOOPS)
     h2d = allsum(tile_bytes)
     eng.close()
     if dist:
@@ -178,7 +180,7 @@ def run_ours(a) -> dict | None:
         "config": {"model": "3x3 gaussian blur /16 (reference default filter)", "image": f"{WIDTH}x{HEIGHT} RGB",
                    "iterations_per_step": LOOPS, "global_batch": 1, "seq_len": WIDTH * HEIGHT,
                    "parallelism": f"2-D block decomposition {g.grid_rows}x{g.grid_cols} over {a.gpus} GPU(s)",
-                   "backend": a.backend, "plan": dict(plan.__dict__) if plan else {},
+                   "backend": a.backend, "kernel_mode": kmode, "plan": dict(plan.__dict__) if plan else {},
                    "cache": f"inputs rotate through a device pool of {pool} images/GPU "
                             f"({pool * tile_bytes >> 20} MiB > L2 {l2 >> 20} MiB); no L2 flush needed",
                    "timed_region": "pool->tile device copy + halo protocol + all iterations of every step",

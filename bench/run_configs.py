@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""BASELINE.json configs on N GPUs (run under torchrun, or plain python for N=1).
+
+  config 2: 1920x2520   RGB  3x3 blur (gaussian)   100 iterations
+  config 3: 16384x16384 grey 3x3 edge-detect        500 iterations
+  config 4: 32768x32768 RGB  3x3 sharpen            100 iterations   (3.2 GB image)
+
+``edge`` is the reference's own table (1 4 1 / 4 8 4 / 1 4 1 over 28 -> exact-fp32 path);
+``--filter laplacian`` gives a true edge detector on the integer path. Images are synthetic,
+generated per tile on the device. Prints one JSON line per run with Mpx/s (device-timed, max over
+ranks), exposed halo wait, and the roofline terms (HBM traffic at the measured copy bandwidth, halo
+bytes over NVLink at the measured peer bandwidth, integer-ALU bound of the SWAR kernels).
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {2: (1920, 2520, 3, "gaussian", 100), 3: (16384, 16384, 1, "edge", 500),
+           4: (32768, 32768, 3, "sharpen", 100)}
+HBM_GBS, NVLINK_GBS = 6570.9, 770.0          # MEASURED_PEAKS.json / B200_PROFILING.md
+ALU_BYTES_PER_CLK = {"sep121-swar": 34.0, "int-swar": 16.0, "f32-exact": 6.0}   # per SM, DESIGN.md
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4])
+    ap.add_argument("--loops", type=int, default=0, help="override the iteration count (0: as specified)")
+    ap.add_argument("--filter", default="")
+    ap.add_argument("--backend", default="fused")
+    ap.add_argument("--mode", default="auto")
+    ap.add_argument("--halo-depth", type=int, default=0)
+    ap.add_argument("--reps", type=int, default=2)
+    a = ap.parse_args()
+    W, H, C, filt, loops = CONFIGS[a.config]
+    loops = a.loops or loops
+    filt = a.filter or filt
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from parallel_convolution_b200 import ConvEngine
+    from parallel_convolution_b200.ops import cuda as K
+    eng = ConvEngine(width=W, height=H, channels=C, filter=filt, backend=a.backend, mode=a.mode,
+                     halo_depth=a.halo_depth or None, device=local)
+    best = None
+    for _ in range(a.reps + 1):      # first run = warm-up
+        eng.load_synthetic(7)
+        rep = eng.iterate(loops)
+        if best is None or rep.elapsed_ms < best.elapsed_ms:
+            best = rep
+    if eng.rank == 0:
+        g = eng.grid
+        k = best.plan.get("k", 1) or 1
+        img_bytes = W * H * C
+        t = best.elapsed_ms * 1e-3
+        mpx = W * H * loops / t / 1e6
+        hbm_s = 2.0 * img_bytes / k * loops / world / (HBM_GBS * 1e9)
+        halo_s = g.halo_bytes_per_iteration(0, k) * (loops / k) / (NVLINK_GBS * 1e9)
+        clk = 1.9e9
+        alu_s = img_bytes * loops / world / (ALU_BYTES_PER_CLK[eng.filter.kind_name] * K.sm_count() * clk)
+        roof = max(hbm_s, halo_s, alu_s)
+        print(json.dumps({"config": a.config, "image": f"{W}x{H}x{C}", "filter": eng.filter.name,
+                          "path": eng.filter.kind_name, "loops": loops, "gpus": world,
+                          "grid": f"{g.grid_rows}x{g.grid_cols}", "backend": eng.backend, "plan": best.plan,
+                          "seconds": round(t, 6), "mpx_s": round(mpx, 1), "launches": best.launches,
+                          "exposed_halo_wait_us_max": round(best.max_wait_us, 1),
+                          "roofline_s": {"hbm": round(hbm_s, 6), "nvlink_halo": round(halo_s, 9),
+                                         "int_alu": round(alu_s, 6)},
+                          "fraction_of_roofline": round(roof / t, 3)}), flush=True)
+    eng.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
