@@ -73,6 +73,9 @@ int pconv_stream_run(const pconv_stream_params_t* pp, int nranks, const int32_t*
 // then announce signal_value to them. Brackets host/device copies into a tile buffer between runs
 // so that back-to-back steps need no host barrier (bench.py, streaming ingest).
 int pconv_sync_launch(const pconv_sync_t* s, void* stream);
+// Force the lazy module load of the kernel a plan will use (cudaFuncGetAttributes), so that the
+// first timed run does not pay ~10 ms of one-time SASS loading. resident != 0: resident kernel.
+int pconv_kernel_prepare(int kind, int C, int R, int resident);
 // Band heights compiled for a filter kind; returns the count, fills out[0..cap).
 int pconv_stream_band_heights(int kind, int* out, int cap);
 

@@ -282,3 +282,12 @@ extern "C" int pconv_resident_launch(const pconv_resident_params_t* p, void* str
     if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "resident_kernel launch");
     return 0;
 }
+
+extern "C" int pconv_resident_prepare(int kind, int C, int R) {
+    ResidentFn fn = pick_kernel(kind, C, R);
+    if (!fn) return pconv_rt::fail("unsupported (filter kind, channels, band height) combination");
+    cudaFuncAttributes at;
+    cudaError_t e = cudaFuncGetAttributes(&at, (const void*)fn);
+    if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "cudaFuncGetAttributes");
+    return 0;
+}

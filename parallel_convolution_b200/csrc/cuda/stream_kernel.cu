@@ -268,3 +268,15 @@ extern "C" int pconv_sync_launch(const pconv_sync_t* s, void* stream) {
     if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "sync_kernel launch");
     return 0;
 }
+
+extern "C" int pconv_resident_prepare(int kind, int C, int R);   // resident_kernel.cu
+
+extern "C" int pconv_kernel_prepare(int kind, int C, int R, int resident) {
+    if (resident) return pconv_resident_prepare(kind, C, R);
+    KernelFn fn = pick_kernel(kind, C, R);
+    if (!fn) return pconv_rt::fail("unsupported (filter kind, channels, band height) combination");
+    cudaFuncAttributes at;
+    cudaError_t e = cudaFuncGetAttributes(&at, (const void*)fn);
+    if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "cudaFuncGetAttributes");
+    return 0;
+}

@@ -60,6 +60,7 @@ def lib() -> C.CDLL:
     L.pconv_stream_run.argtypes = [C.POINTER(StreamParams), C.c_int, C.POINTER(C.c_int32), C.c_int,
                                    C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_void_p), vp]
     L.pconv_sync_launch.argtypes = [C.POINTER(Sync), vp]
+    L.pconv_kernel_prepare.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
     L.pconv_stream_band_heights.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int]
     if hasattr(L, "pconv_resident_launch"):
         L.pconv_resident_launch.argtypes = [C.POINTER(ResidentParams), vp]
@@ -262,6 +263,10 @@ def unpack_rect(tile: int, pitch: int, row0: int, byte0: int, rows: int, nbytes:
                 stream: int) -> None:
     _check(lib().pconv_cuda_unpack_rect(tile, pitch, row0, byte0, rows, nbytes, dense, stream),
            "unpack_rect")
+
+
+def kernel_prepare(kind: int, channels: int, band: int, resident: bool = False) -> None:
+    _check(lib().pconv_kernel_prepare(kind, channels, band, 1 if resident else 0), "kernel_prepare")
 
 
 def stream_launch(p: StreamParams, stream: int) -> None:

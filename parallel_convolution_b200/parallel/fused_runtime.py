@@ -263,7 +263,19 @@ class FusedRuntime:
             K.stream_sync(self._pipe["s_in"])
             K.stream_sync(self._pipe["s_out"])
 
+    def prepare(self, loops: int) -> None:
+        """Plan and force the module load of the kernel that ``loops`` will use (one-time cost)."""
+        if loops <= 0:
+            return
+        resident = self.choose_mode(loops) == "resident"
+        plan = self.resident_plan(loops) if resident else self.plan(loops)
+        key = (plan.R, resident)
+        if key not in getattr(self, "_prepared", set()):
+            K.kernel_prepare(self.filt.kind, self.grid.channels, plan.R, resident)
+            self._prepared = getattr(self, "_prepared", set()) | {key}
+
     def run(self, loops: int, rep, sync: bool = True) -> None:
+        self.prepare(loops)
         for d in self.drivers.values():
             d.reset_status()
         self._barrier()               # every rank's input tile is in place

@@ -187,6 +187,8 @@ class NcclRuntime:
 
     def run(self, loops: int, rep, sync: bool = True) -> None:
         torch = self.torch
+        if loops > 0:
+            K.kernel_prepare(self.filt.kind, self.grid.channels, self.plan(loops).R, False)
         if self.world > 1:
             torch.cuda.synchronize()
             self.dist.barrier()
