@@ -168,8 +168,8 @@ resident_kernel(const __grid_constant__ ResidentArgs A) {
         }
         // 5. iterate
         const int kb = min(k, A.loops - b * k);
-        if (masked) region_iterate<KIND, C, R, true>(rows, eb, kb, cmask, rowmask, A.f);
-        else region_iterate<KIND, C, R, false>(rows, eb, kb, cmask, rowmask, A.f);
+        if (masked) region_iterate<KIND, C, R, true>(rows, eb, kb, cmask, rowmask, need_cols, A.f);
+        else region_iterate<KIND, C, R, false>(rows, eb, kb, cmask, rowmask, need_cols, A.f);
         __syncthreads();  // edge buffers: next block restarts at parity 0
         lap(t_comp);
     }

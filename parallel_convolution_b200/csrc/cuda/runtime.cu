@@ -8,6 +8,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -86,6 +87,10 @@ int fail_cuda(cudaError_t e, const char* where) {
 int sm_count() { return info().sms; }
 int max_optin_smem() { return info().smem_optin; }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+    static const bool on = [] { const char* v = std::getenv("PCONV_PDL"); return !(v && v[0] == '0'); }();
+    return on;
+}
 
 void make_filter_dev(const pconv_filter_t& f, pconv::FilterDev* out) {
     std::memset(out, 0, sizeof(*out));

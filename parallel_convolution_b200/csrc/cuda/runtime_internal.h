@@ -14,6 +14,7 @@ int fail_cuda(cudaError_t e, const char* where);    // records "where: cudaGetEr
 int sm_count();
 int max_optin_smem();
 void count_launch();
+bool pdl_enabled();   // PCONV_PDL=0 disables programmatic dependent launch
 void make_filter_dev(const pconv_filter_t& f, pconv::FilterDev* out);
 
 }  // namespace pconv_rt

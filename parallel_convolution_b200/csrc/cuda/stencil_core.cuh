@@ -97,6 +97,8 @@ struct Sep121Path {
             uE[j] = nE; uO[j] = nO;
         }
     }
+    // push row r+1 when output row r lies outside the image (it stays zero): state update only
+    __device__ __forceinline__ void skip(const uint4& w) { prime1(w); }
     // push row r+1, return output row r
     __device__ __forceinline__ uint4 push(const uint4& w) {
         const uint32_t x[4] = {w.x, w.y, w.z, w.w};
@@ -333,16 +335,28 @@ __device__ __forceinline__ uint4 apply_mask(uint4 o, const uint4& cmask, uint32_
     return o;
 }
 
+// MASKED variant (CTAs touching the image border): rows outside the image are not computed at all —
+// the warp-uniform branch skips the horizontal pass and the row stays zero, so a border warp does
+// LESS work than an interior one instead of pacing the CTA; the column mask is only applied in
+// CTAs that actually contain out-of-image columns (need_cols, CTA-uniform).
 template <int C, int R, bool MASKED>
 __device__ __forceinline__ void band_sep121(uint4 (&rows)[R], const uint4& top, const uint4& bottom,
-                                            const uint4& cmask, uint32_t rowmask, const FilterDev& f) {
+                                            const uint4& cmask, uint32_t rowmask, bool need_cols,
+                                            const FilterDev& f) {
     Sep121Path<C> p(f);
     p.prime0(top);
     p.prime1(rows[0]);
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-        const uint4 o = p.push(i + 1 < R ? rows[i + 1] : bottom);
-        rows[i] = apply_mask<MASKED>(o, cmask, rowmask, i);
+        const uint4& nxt = i + 1 < R ? rows[i + 1] : bottom;
+        if (!MASKED || ((rowmask >> i) & 1u)) {
+            uint4 o = p.push(nxt);
+            if (MASKED && need_cols) { o.x &= cmask.x; o.y &= cmask.y; o.z &= cmask.z; o.w &= cmask.w; }
+            rows[i] = o;
+        } else {
+            p.skip(nxt);
+            rows[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
 }
 
@@ -371,8 +385,9 @@ __device__ __forceinline__ void band_phased(uint4 (&rows)[R], const uint4& top, 
 
 template <int KIND, int C, int R, bool MASKED>
 __device__ __forceinline__ void band_iterate(uint4 (&rows)[R], const uint4& top, const uint4& bottom,
-                                             const uint4& cmask, uint32_t rowmask, const FilterDev& f) {
-    if constexpr (KIND == PCONV_KIND_SEP121) band_sep121<C, R, MASKED>(rows, top, bottom, cmask, rowmask, f);
+                                             const uint4& cmask, uint32_t rowmask, bool need_cols,
+                                             const FilterDev& f) {
+    if constexpr (KIND == PCONV_KIND_SEP121) band_sep121<C, R, MASKED>(rows, top, bottom, cmask, rowmask, need_cols, f);
     else if constexpr (KIND == PCONV_KIND_INT) band_phased<IntPath, C, R, MASKED>(rows, top, bottom, cmask, rowmask, f);
     else band_phased<F32Path, C, R, MASKED>(rows, top, bottom, cmask, rowmask, f);
 }
@@ -388,7 +403,7 @@ struct EdgeBuffers {
 // warp is still reading.
 template <int KIND, int C, int R, bool MASKED>
 __device__ __forceinline__ void region_iterate(uint4 (&rows)[R], EdgeBuffers& eb, int k,
-                                               const uint4& cmask, uint32_t rowmask,
+                                               const uint4& cmask, uint32_t rowmask, bool need_cols,
                                                const FilterDev& f) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
@@ -399,7 +414,7 @@ __device__ __forceinline__ void region_iterate(uint4 (&rows)[R], EdgeBuffers& eb
         __syncthreads();
         const uint4 top = warp > 0 ? eb.row[par][warp - 1][1][lane] : zero;
         const uint4 bottom = warp < kWarps - 1 ? eb.row[par][warp + 1][0][lane] : zero;
-        band_iterate<KIND, C, R, MASKED>(rows, top, bottom, cmask, rowmask, f);
+        band_iterate<KIND, C, R, MASKED>(rows, top, bottom, cmask, rowmask, need_cols, f);
     }
 }
 

@@ -54,6 +54,13 @@ stream_kernel(const __grid_constant__ StreamArgs A) {
     const int ntiles = A.ntx * A.nty;
     const int64_t tile_row_end = g.row_lo[2], tile_cb_end = g.cb_lo[2];
 
+    // Programmatic dependent launch: this grid may be scheduled while the previous launch of the
+    // run is still draining (its CTAs occupy whole SMs, so ours start one by one as theirs exit);
+    // nothing above touches memory the previous launch writes. Let the next launch do the same to
+    // us, then wait for the previous grid to complete and flush before reading its output.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int ti = tile / A.ntx, tj = tile % A.ntx;
         const int64_t gr0 = g.row_lo[1] + (int64_t)ti * A.TH - k;     // image row of region row 0
@@ -94,8 +101,8 @@ stream_kernel(const __grid_constant__ StreamArgs A) {
         const bool masked = need_cols || gr0 < 0 || gr0 + RH > g.img_rows;  // CTA-uniform
 
         // ---- k fused iterations in registers ------------------------------------------------------
-        if (masked) region_iterate<KIND, C, R, true>(rows, eb, k, cmask, rowmask, A.f);
-        else region_iterate<KIND, C, R, false>(rows, eb, k, cmask, rowmask, A.f);
+        if (masked) region_iterate<KIND, C, R, true>(rows, eb, k, cmask, rowmask, need_cols, A.f);
+        else region_iterate<KIND, C, R, false>(rows, eb, k, cmask, rowmask, need_cols, A.f);
 
         // ---- store the interior straight from registers ------------------------------------------
         const bool col_in = (16 * lane >= A.HB) && (16 * lane < A.HB + A.TWB);
@@ -228,8 +235,19 @@ extern "C" int pconv_stream_launch(const pconv_stream_params_t* p, void* stream)
     const int ntiles = a.ntx * a.nty;
     int grid = p->grid > 0 ? p->grid : pconv_rt::sm_count();
     if (grid > ntiles) grid = ntiles;
-    fn<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
-    cudaError_t e;
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pconv_rt::pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, a);
+    if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "stream_kernel launch");
     pconv_rt::count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "stream_kernel launch");

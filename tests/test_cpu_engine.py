@@ -113,3 +113,31 @@ def test_synth_is_decomposition_independent():
     full = host.synth_rect(7, 300, 0, 20, 0, 300)
     part = host.synth_rect(7, 300, 5, 6, 17, 100)
     assert np.array_equal(part, full[5:11, 17:117])
+
+
+REF_GREY = "/root/reference/waterfall_grey_1920_2520.raw"
+REF_RGB = "/root/reference/waterfall_1920_2520.raw"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_GREY), reason="reference data assets not mounted")
+def test_reference_assets_have_the_documented_format():
+    """headerless row-major uint8, 1920 (W) x 2520 (H), 1 / 3 channels."""
+    assert host.file_size(REF_GREY) == 1920 * 2520
+    assert host.file_size(REF_RGB) == 1920 * 2520 * 3
+    strip = host.read_rect(REF_GREY, 1920, 1000, 64, 0, 1920)
+    f = Filter.builtin("gaussian")
+    # a strip of the real image through both CPU implementations
+    assert np.array_equal(host.cpu_run_image(strip, f.spec, 3), host.oracle(strip, f.spec, 3))
+
+
+def test_native_planner_invariants():
+    from parallel_convolution_b200.parallel.plan import plan_resident, plan_stream
+    for rows, cb, C, kind, loops in [(2520, 5760, 3, 2, 100), (2520, 1920, 1, 2, 100), (630, 2880, 3, 1, 7),
+                                     (16384, 16384, 1, 0, 500), (37, 41, 1, 2, 3)]:
+        p = plan_stream(rows, cb, C, kind, loops)
+        assert p.TH + 2 * p.k <= 16 * p.R and p.HB >= p.k * C and p.HB % 16 == 0
+        assert p.TWB + 2 * p.HB == 512 and p.ntx * p.TWB >= cb and p.nty * p.TH >= rows
+        assert sum(p.launches(loops)) == loops
+    r = plan_resident(2520, 5760, 3, 2, 100)
+    assert r is not None and r.ntx * r.nty <= 148 and r.TH >= r.k
+    assert plan_resident(16384, 16384, 1, 2, 100) is None      # does not fit on chip -> stream
