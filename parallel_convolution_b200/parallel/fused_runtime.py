@@ -149,9 +149,12 @@ class FusedRuntime:
             if self.mode == "resident" and self.resident_plan(loops) is None:
                 raise ValueError("resident mode requested but the tile does not fit on chip")
             return self.mode
-        # "auto": the streaming launches win on B200 today (0.47 vs 0.51 ms for the headline config on
-        # one GPU, 0.31 vs 0.32 ms on two: one in-kernel exchange still costs about as much as a
-        # relaunch + reload). The persistent kernel stays one flag away.
+        # "auto", from measurements on B200 (profiles/README.md): on 1-2 GPUs one in-kernel exchange
+        # costs about as much as a relaunch + reload, and streaming wins by 4-8 % (0.47 vs 0.51 ms on
+        # one GPU, 0.31 vs 0.32 ms on two); from 4 GPUs up the per-launch cross-GPU skew dominates and
+        # the persistent kernel wins (0.21 vs 0.26 ms on eight).
+        if self.world >= 4 and self.resident_plan(loops) is not None:
+            return "resident"
         return "stream"
 
     def _enqueue_resident(self, loops: int) -> tuple[StreamPlan, int]:
