@@ -54,10 +54,7 @@ def main():
             row["halo_bytes_per_exchange"] = eng.grid.halo_bytes_per_iteration(0, a.halo_depth)
             row.setdefault("waits", {})[be] = round(rep.max_wait_us, 1)
             eng.close()
-        # the same tile alone on this GPU (no neighbours): the compute-only floor
-        if rank == 0:
-            os.environ["PCONV_SOLO"] = "1"
-        # every rank builds a private single-tile engine without the process group
+        # the same tile alone on this GPU (no neighbours, no process group): the compute-only floor
         from parallel_convolution_b200.parallel.decomposition import TileGrid
         from parallel_convolution_b200.parallel.fused import VirtualCluster
         from parallel_convolution_b200.models.filters import Filter

@@ -58,6 +58,7 @@ class RunReport:
     sum_wait_us: float = 0.0
     waits: int = 0
     watchdog: bool = False
+    probe: dict = field(default_factory=dict)   # resident kernel: in-kernel phase times of one interior CTA
 
     def mpixels_per_s(self, width: int, height: int) -> float:
         return width * height * self.loops / max(self.elapsed_ms, 1e-9) / 1e3

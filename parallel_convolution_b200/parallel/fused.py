@@ -16,7 +16,7 @@ local pointers) — the way multi-GPU logic is tested on a 1-GPU box (SURVEY.md 
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 
@@ -95,7 +95,6 @@ class TileDriver:
         self.pitch, self.stream = pitch, stream
         self.timeout_ns = int(timeout_ms * 1e6)
         self.tile = grid.tile(rank)
-        self.epoch = 0                      # last epoch signalled
         self.inject_delay_ns = 0            # fault injection (tests / --inject-*)
         self.inject_drop_signal = False
         self._geom = self._geometry()
@@ -167,17 +166,6 @@ class TileDriver:
         p.sync.timeout_ns = self.timeout_ns
         p.sync.inject_drop_signal = 1 if self.inject_drop_signal else 0
         return p
-
-    def enqueue(self, plan: StreamPlan, k: int, src_parity: int, first: bool,
-                multi: bool) -> None:
-        """One launch of ``k`` fused iterations reading ``bufs[src_parity]``."""
-        if multi:
-            self.epoch += 1
-            wait = 0 if first else self.epoch - 1
-            signal = self.epoch
-        else:
-            wait = signal = 0
-        K.stream_launch(self._params(plan, k, src_parity, wait, signal), self.stream)
 
     def sync_params(self, wait: int, signal: int, bank: int = 0) -> K.Sync:
         """Parameters of a stand-alone protocol step on flag bank 0 (launch epochs) or 1 (inputs)."""

@@ -18,7 +18,7 @@ import numpy as np
 from ..models.filters import Filter
 from ..ops import cuda as K
 from .decomposition import TileGrid
-from .fused import (RankMemory, STATUS_WORDS, TileDriver, make_plan, make_resident_plan,
+from .fused import (RankMemory, TileDriver, make_plan, make_resident_plan,
                     tile_pitch)
 from .plan import StreamPlan
 
@@ -113,17 +113,13 @@ class FusedRuntime:
         return self._plans[loops]
 
     # -- in-stream input hand-over (no host barrier between back-to-back steps) -------------------
-    def _sync_params(self, d: TileDriver, wait: int, signal: int) -> K.Sync:
-        p = d._params(self.plan(1), 1, 0, wait, signal)
-        return p.sync
-
     def begin_input(self) -> int:
         """Enqueue: wait until every neighbour finished the previous run (they may still be reading
         my buffers). Call before overwriting a tile buffer in-stream. Returns kernels launched."""
         if not self.multi or self.epoch == 0:
             return 0
         for d in self.drivers.values():
-            K.sync_launch(self._sync_params(d, self.epoch, 0), self.stream)
+            K.sync_launch(d.sync_params(self.epoch, 0), self.stream)
         return len(self.drivers)
 
     def end_input(self) -> int:
@@ -132,7 +128,7 @@ class FusedRuntime:
             return 0
         self.epoch += 1
         for d in self.drivers.values():
-            K.sync_launch(self._sync_params(d, 0, self.epoch), self.stream)
+            K.sync_launch(d.sync_params(0, self.epoch), self.stream)
         self._first_wait = self.epoch
         return len(self.drivers)
 
@@ -299,6 +295,8 @@ class FusedRuntime:
             rep.max_wait_us = max(rep.max_wait_us, mx)
             rep.sum_wait_us += sm
             rep.waits += nw
+            if getattr(d, "probe", None) and d.probe.get("exchanges"):
+                rep.probe = d.probe
         self._barrier()
         if rep.watchdog:
             raise RuntimeError("halo watchdog fired: a neighbouring rank never signalled "

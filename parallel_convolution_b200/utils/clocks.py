@@ -9,7 +9,6 @@ from __future__ import annotations
 import statistics
 import subprocess
 import threading
-import time
 
 _REASONS = {
     0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",

@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--filter", default="gaussian")
     ap.add_argument("--halo-depth", type=int, default=0)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--mode", default="auto")
+    ap.add_argument("--grid", default="")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -38,8 +40,9 @@ def main():
     g_rows = host.synth_rect(42, a.width * a.channels, 0, a.height, 0, a.width * a.channels)
     img = g_rows.reshape(a.height, a.width, a.channels) if a.channels > 1 else g_rows
     ref = host.cpu_run_image(img, f.spec, a.loops) if rank == 0 else None
+    grid = tuple(int(v) for v in a.grid.split("x")) if a.grid else None
     eng = ConvEngine(width=a.width, height=a.height, channels=a.channels, filter=f, backend=a.backend,
-                     halo_depth=a.halo_depth or None)
+                     halo_depth=a.halo_depth or None, mode=a.mode, grid=grid)
     ok = True
     for rep in range(a.reps):     # twice: exercises epoch continuity / buffer reuse across runs
         eng.load_synthetic(42)
@@ -51,7 +54,7 @@ def main():
             print(f"[dist_check] rep={rep} backend={a.backend} world={dist.get_world_size()} "
                   f"grid={eng.grid.grid_rows}x{eng.grid.grid_cols} filter={f.name} loops={a.loops} "
                   f"elapsed_ms={r.elapsed_ms:.3f} max_wait_us={r.max_wait_us:.1f} waits={r.waits} "
-                  f"plan={r.plan} {'OK' if same else 'MISMATCH ' + str(int((out.reshape(ref.shape) != ref).sum()))}",
+                  f"plan={r.plan} probe={r.probe} {'OK' if same else 'MISMATCH ' + str(int((out.reshape(ref.shape) != ref).sum()))}",
                   flush=True)
     eng.close()
     dist.barrier()

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from parallel_convolution_b200.models.filters import Filter
 from parallel_convolution_b200.ops import cuda as K
 from parallel_convolution_b200.parallel.decomposition import TileGrid
-from parallel_convolution_b200.parallel.fused import VirtualCluster, make_plan
+from parallel_convolution_b200.parallel.fused import VirtualCluster
 
 
 def main():
