@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--mode", default="auto")
     ap.add_argument("--halo-depth", type=int, default=0)
     ap.add_argument("--filter", default=FILTER)
+    ap.add_argument("--no-autotune", action="store_true", help="use the model-based plan as is")
     return ap.parse_args()
 
 
@@ -91,6 +92,12 @@ def run_ours(a) -> dict | None:
     eng = ConvEngine(width=WIDTH, height=HEIGHT, channels=CHANNELS, filter=a.filter,
                      backend=a.backend, mode=a.mode, halo_depth=a.halo_depth or None, device=local,
                      slots=SLOTS if a.backend == "fused" else 1)
+    tuned = {}
+    if not a.no_autotune and a.backend == "fused":
+        try:
+            tuned = eng.autotune(LOOPS)      # untimed: pick (mode, k, R) by measurement on this box
+        except Exception as e:  # noqa: BLE001 - never let the tuner take the benchmark down
+            tuned = {"error": str(e)}
     tile = eng.grid.tile(rank)
     tile_bytes = tile.rows * tile.cols * CHANNELS
     l2 = K.l2_bytes() or (126 << 20)
@@ -180,7 +187,8 @@ def run_ours(a) -> dict | None:
         "config": {"model": "3x3 gaussian blur /16 (reference default filter)", "image": f"{WIDTH}x{HEIGHT} RGB",
                    "iterations_per_step": LOOPS, "global_batch": 1, "seq_len": WIDTH * HEIGHT,
                    "parallelism": f"2-D block decomposition {g.grid_rows}x{g.grid_cols} over {a.gpus} GPU(s)",
-                   "backend": a.backend, "kernel_mode": kmode, "plan": dict(plan.__dict__) if plan else {},
+                   "backend": a.backend, "kernel_mode": kmode,
+                   "autotune": {"tried": tuned.get("tried", [])[:8]} if tuned else "off", "plan": dict(plan.__dict__) if plan else {},
                    "cache": f"inputs rotate through a device pool of {pool} images/GPU "
                             f"({pool * tile_bytes >> 20} MiB > L2 {l2 >> 20} MiB); no L2 flush needed",
                    "timed_region": "pool->tile device copy + halo protocol + all iterations of every step",

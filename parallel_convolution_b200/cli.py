@@ -46,6 +46,8 @@ def build_parser() -> argparse.ArgumentParser:
                    help="single process: decompose over N virtual ranks on one GPU")
     p.add_argument("--grid", default=None, help="tile grid ROWSxCOLS (default: perimeter-minimising)")
     p.add_argument("--halo-depth", type=int, default=None, help="temporal-blocking depth k")
+    p.add_argument("--autotune", action="store_true",
+                   help="fused backend: measure candidate launch plans on this machine before the run")
     p.add_argument("--threads", type=int, default=0, help="cpu backend: OpenMP threads per rank")
     p.add_argument("-o", "--output", default=None)
     p.add_argument("--no-output", action="store_true", help="skip writing the result image")
@@ -109,6 +111,9 @@ def main(argv: list[str] | None = None) -> int:
             for r, d in eng._impl.drivers.items():
                 d.inject_drop_signal = (r == a.inject_drop_signal)
         done = 0
+        if a.autotune and a.loops > 0:
+            with nvtx_range("pconv:autotune"):
+                eng.autotune(min(a.loops, a.checkpoint_every) if a.checkpoint_every > 0 else a.loops)
         with nvtx_range("pconv:load"):
             state = ckpt.load_state(out_path) if a.resume else None
             if state is not None:

@@ -190,6 +190,13 @@ class ConvEngine:
             self._impl.synth(seed)
 
     # -- compute -------------------------------------------------------------------------------------
+    def autotune(self, loops: int) -> dict:
+        """Fused backend: measure candidate launch plans for ``loops`` iterations on this machine
+        and adopt the fastest (a few ms; overwrites the loaded tiles — call before loading input)."""
+        if self.backend == "fused" and hasattr(self._impl, "autotune"):
+            return self._impl.autotune(loops)
+        return {}
+
     def iterate(self, loops: int, sync: bool = True) -> RunReport:
         """Apply the filter ``loops`` times to the loaded tiles. Device-timed for GPU backends."""
         rep = RunReport(loops=loops, backend=self.backend)

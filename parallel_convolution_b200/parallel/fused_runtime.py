@@ -140,7 +140,93 @@ class FusedRuntime:
                 peers=self.world > 1)
         return self._rplans[loops]
 
+    # -- on-device autotuning ----------------------------------------------------------------------
+    def autotune(self, loops: int, max_candidates: int = 14, reps: int = 2) -> dict:
+        """Measure candidate (mode, k, R) plans for ``loops`` iterations on this machine and keep the
+        fastest. The model-based planner is good at ranking but blind to box-specific effects
+        (launch gaps, cross-GPU skew); a few milliseconds of measurement settle it. Collective: every
+        rank times the same candidates in the same order and the decision uses the max over ranks,
+        so all ranks adopt the same plan. Overwrites the tile buffers with synthetic data — call it
+        before loading real input."""
+        if loops <= 0:
+            return {}
+        base_s, base_r = self.plan(loops), (self.resident_plan(loops) if self.mode != "stream" else None)
+        cands: list[tuple[str, StreamPlan]] = []
+
+        def add(mode: str, k: int, R: int) -> None:
+            try:
+                if mode == "stream":
+                    p = make_plan(self.grid, self.filt, loops, k, self.sms, self.bands, R)
+                else:
+                    p = make_resident_plan(self.grid, self.filt, loops, k, self.sms // len(self.local_ranks),
+                                           self.bands, R, peers=self.world > 1)
+            except ValueError:
+                return
+            if p is not None and (mode, p) not in cands:
+                cands.append((mode, p))
+
+        modes = [m for m in ("stream", "resident") if self.mode in ("auto", m)]
+        for mode in modes:
+            base = base_s if mode == "stream" else base_r
+            if base is None:
+                continue
+            cands.append((mode, base))
+            for k in sorted({max(1, base.k - 2), max(1, base.k - 1), base.k + 1, base.k + 2, base.k + 5,
+                             max(1, base.k // 2), base.k * 2} - {base.k}):
+                if self.halo_depth or k > loops:
+                    continue
+                for R in ([base.R] + [b for b in self.bands if b != base.R]):
+                    if self.band and R != self.band:
+                        continue
+                    add(mode, k, R)
+        # rank by the model, measure the most promising ones
+        cands.sort(key=lambda mp: mp[1].est_us_per_launch * (1 if mp[0] == "resident" else -(-loops // mp[1].k)))
+        cands = cands[:max_candidates]
+        saved = (self.mode, dict(self._plans), dict(self._rplans))
+        results = []
+        for mode, p in cands:
+            self.mode = mode
+            (self._plans if mode == "stream" else self._rplans)[loops] = p
+            best = None
+            try:
+                self.prepare(loops)
+                for _ in range(reps + 1):
+                    for d in self.drivers.values():
+                        d.synth(17, 2 * self.slot)
+                    self.parity = 0
+                    self._barrier()
+                    e0, e1 = K.Event(), K.Event()
+                    e0.record(self.stream)
+                    self.enqueue(loops)
+                    e1.record(self.stream)
+                    e1.synchronize()
+                    ms = e0.elapsed_ms(e1)
+                    best = ms if best is None else min(best, ms)
+                self._barrier()
+            except Exception:          # a candidate the kernels reject is simply not a candidate
+                best = None
+            if best is not None and self.world > 1:
+                import torch
+                t = torch.tensor([best], dtype=torch.float64, device="cuda")
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+                best = float(t.item())
+            if best is not None:
+                results.append((best, mode, p))
+        self.mode, self._plans, self._rplans = saved
+        if not results:
+            return {}
+        results.sort(key=lambda r: r[0])
+        ms, mode, p = results[0]
+        self._tuned = getattr(self, "_tuned", {})
+        self._tuned[loops] = mode
+        (self._plans if mode == "stream" else self._rplans)[loops] = p
+        return {"mode": mode, "plan": dict(p.__dict__), "ms": ms,
+                "tried": [(round(r[0], 4), r[1], r[2].k, r[2].R) for r in results]}
+
     def choose_mode(self, loops: int) -> str:
+        tuned = getattr(self, "_tuned", {}).get(loops)
+        if tuned and self.mode == "auto":
+            return tuned
         if self.mode in ("stream", "resident"):
             if self.mode == "resident" and self.resident_plan(loops) is None:
                 raise ValueError("resident mode requested but the tile does not fit on chip")

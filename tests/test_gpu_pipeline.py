@@ -40,3 +40,15 @@ def test_pipelined_steps_match_oracle(rng, workers, mode):
                 t = eng.grid.tile(r)
                 assert np.array_equal(tile, ref[t.row0:t.row0 + t.rows, t.col0 * C:(t.col0 + t.cols) * C]), \
                     (workers, mode, i, r)
+
+
+@pytest.mark.parametrize("workers", [1, 4])
+def test_autotune_keeps_results_exact(rng, workers):
+    from parallel_convolution_b200 import ConvEngine
+    img = random_image(rng, 360, 480, 3)
+    f = Filter.builtin("gaussian")
+    with ConvEngine(width=480, height=360, channels=3, filter=f, backend="fused", workers=workers) as eng:
+        info = eng.autotune(20)
+        assert info and info["mode"] in ("stream", "resident") and len(info["tried"]) >= 2
+        out = eng.run(img, 20)
+    assert np.array_equal(out, host.cpu_run_image(img, f.spec, 20))
