@@ -21,8 +21,6 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {2: (1920, 2520, 3, "gaussian", 100), 3: (16384, 16384, 1, "edge", 500),
            4: (32768, 32768, 3, "sharpen", 100)}
-HBM_GBS, NVLINK_GBS = 6570.9, 770.0          # MEASURED_PEAKS.json / B200_PROFILING.md
-ALU_BYTES_PER_CLK = {"sep121-swar": 34.0, "int-swar": 16.0, "f32-exact": 6.0}   # per SM, DESIGN.md
 
 
 def main():
@@ -62,19 +60,16 @@ def main():
         img_bytes = W * H * C
         t = best.elapsed_ms * 1e-3
         mpx = W * H * loops / t / 1e6
-        hbm_s = 2.0 * img_bytes / k * loops / world / (HBM_GBS * 1e9)
-        halo_s = g.halo_bytes_per_iteration(0, k) * (loops / k) / (NVLINK_GBS * 1e9)
-        clk = 1.9e9
-        alu_s = img_bytes * loops / world / (ALU_BYTES_PER_CLK[eng.filter.kind_name] * K.sm_count() * clk)
-        roof = max(hbm_s, halo_s, alu_s)
+        from parallel_convolution_b200.utils import roofline
+        roof = roofline.terms(W, H, C, loops, world, k, eng.filter.kind_name,
+                              g.halo_bytes_per_iteration(0, k), K.sm_count())
+        frac = roofline.fraction(t, roof)
         print(json.dumps({"config": a.config, "image": f"{W}x{H}x{C}", "filter": eng.filter.name,
                           "path": eng.filter.kind_name, "loops": loops, "gpus": world,
                           "grid": f"{g.grid_rows}x{g.grid_cols}", "backend": eng.backend, "plan": best.plan,
                           "seconds": round(t, 6), "mpx_s": round(mpx, 1), "launches": best.launches,
                           "exposed_halo_wait_us_max": round(best.max_wait_us, 1),
-                          "roofline_s": {"hbm": round(hbm_s, 6), "nvlink_halo": round(halo_s, 9),
-                                         "int_alu": round(alu_s, 6)},
-                          "fraction_of_roofline": round(roof / t, 3)}), flush=True)
+                          "roofline": roof, "fraction_of_binding_roofline": round(frac, 3)}), flush=True)
     eng.close()
     if dist:
         dist.barrier()

@@ -86,6 +86,17 @@ def build_host(force: bool = False) -> Path:
     return HOST_LIB
 
 
+def build_host_sanitized() -> Path:
+    """Host library instrumented with AddressSanitizer + UndefinedBehaviorSanitizer (debug aid;
+    scripts/host_sanitize.sh runs the CPU tests against it with LD_PRELOAD=libasan)."""
+    LIB.mkdir(exist_ok=True)
+    out = LIB / "libpconv_host_asan.so"
+    srcs = [str(CSRC / s) for s in HOST_SOURCES] + [str(CSRC / HOST_ORACLE)]
+    _run([CXX, "-std=c++17", "-fPIC", "-O1", "-g", "-ffp-contract=off", "-fopenmp", "-fno-omit-frame-pointer",
+          "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-shared", "-o", str(out), *srcs])
+    return out
+
+
 def build_cuda(force: bool = False) -> Path:
     LIB.mkdir(exist_ok=True)
     srcs = [CSRC / s for s in CUDA_SOURCES if (CSRC / s).exists()]

@@ -148,14 +148,20 @@ def main(argv: list[str] | None = None) -> int:
             verified = _verify(eng, a, channels, out_path)
         if rank == 0:
             if a.json:
+                from .utils import roofline
                 g = eng.grid
                 mpx = a.width * a.height * a.loops / max(elapsed_ms, 1e-9) / 1e3
+                kk = rep.plan.get("k", 1) or 1
+                roof = roofline.terms(a.width, a.height, channels, a.loops, g.workers, kk,
+                                      eng.filter.kind_name, g.halo_bytes_per_iteration(0, kk))
                 print(json.dumps({
                     "seconds": elapsed_ms / 1e3, "mpixels_per_s": mpx, "iterations": a.loops,
                     "backend": eng.backend, "filter": eng.filter.describe(), "grid": g.describe(),
                     "workers": g.workers, "plan": rep.plan, "kernel_launches": launches,
                     "exposed_halo_wait_us": {"max": rep.max_wait_us, "sum": rep.sum_wait_us, "waits": rep.waits},
                     "halo_bytes_per_exchange_rank0": g.halo_bytes_per_iteration(0, rep.plan.get("k", 1) or 1),
+                    "roofline": roof, "fraction_of_binding_roofline": round(
+                        roofline.fraction(elapsed_ms / 1e3, roof), 4) if a.loops else None,
                     "output": None if a.no_output else out_path, "verified": verified}))
             else:
                 print(f"{elapsed_ms / 1e3:f}")

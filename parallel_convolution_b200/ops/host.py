@@ -47,7 +47,7 @@ class PlanResult(C.Structure):
 
 @lru_cache(maxsize=1)
 def lib() -> C.CDLL:
-    path = _build.ensure_host()
+    path = os.environ.get("PCONV_HOST_LIB") or _build.ensure_host()   # override: sanitizer builds
     L = C.CDLL(os.fspath(path))
     i64, u8p, fsp = C.c_int64, C.c_void_p, C.POINTER(FilterSpec)
     L.pconv_filter_from_int.argtypes = [C.POINTER(C.c_int32), C.c_double, fsp]
