@@ -49,6 +49,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--autotune", action="store_true",
                    help="fused backend: measure candidate launch plans on this machine before the run")
     p.add_argument("--threads", type=int, default=0, help="cpu backend: OpenMP threads per rank")
+    p.add_argument("--batch", default=None, metavar="LIST",
+                   help="text file with one raw image path per line (all of the given shape): filter them "
+                        "all, streaming through the pipelined slots; outputs blur_<name> (in -o DIR if given)")
     p.add_argument("-o", "--output", default=None)
     p.add_argument("--no-output", action="store_true", help="skip writing the result image")
     p.add_argument("--synthetic", type=int, default=None, metavar="SEED",
@@ -106,10 +109,22 @@ def main(argv: list[str] | None = None) -> int:
         with nvtx_range("pconv:setup"):
             eng = ConvEngine(width=a.width, height=a.height, channels=channels, filter=a.filter,
                              backend=a.backend, workers=a.workers, grid=grid, halo_depth=a.halo_depth,
-                             mode=a.mode, threads=a.threads, timeout_ms=a.timeout_ms)
+                             mode=a.mode, threads=a.threads, timeout_ms=a.timeout_ms,
+                             slots=3 if a.batch else 1)
         if a.inject_drop_signal is not None and hasattr(eng._impl, "drivers"):
             for r, d in eng._impl.drivers.items():
                 d.inject_drop_signal = (r == a.inject_drop_signal)
+        if a.batch:
+            with open(a.batch) as f:
+                paths = [ln.strip() for ln in f if ln.strip()]
+            info = eng.run_batch(paths, a.loops, a.output)
+            if rank == 0:
+                print(json.dumps(info) if a.json else f"{info['seconds']:f}")
+            eng.close()
+            if dist:
+                dist.barrier()
+                dist.destroy_process_group()
+            return 0
         done = 0
         if a.autotune and a.loops > 0:
             with nvtx_range("pconv:autotune"):

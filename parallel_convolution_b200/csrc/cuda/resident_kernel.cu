@@ -4,7 +4,7 @@
 //
 //   exchange b (b = 1, 2, ...):
 //     1. each CTA stores the border strips of its interior into tile buffer parity (b & 1)
-//     2. __threadfence_system, then st.release.sys of epoch_base+b to its own flag — and, for CTAs
+//     2. st.release (gpu scope) of epoch_base+b to its own flag — and, for CTAs
 //        on the edge of the GPU's tile, to the mirrored ring entry in the neighbour GPU's flag
 //        array (peer store over NVLink)
 //     3. eight threads spin (ld.acquire.sys) on the flags of the eight surrounding CTAs — local
@@ -131,19 +131,17 @@ resident_kernel(const __grid_constant__ ResidentArgs A) {
             lap(t_pub);
             // 2. announce epoch b: own flag + mirrored ring entries on neighbouring GPUs
             const uint32_t epoch = A.epoch_base + (uint32_t)b;
-            if (threadIdx.x == 0) {   // local consumers: gpu scope is enough (and much cheaper)
-                __threadfence();
+            // The release store alone publishes the strips: the CTA's stores happen-before it through
+            // the barrier above (causality is cumulative), so no separate MEMBAR.SC is issued.
+            if (threadIdx.x == 0)     // local consumers: gpu scope is enough (and much cheaper)
                 st_release_gpu(A.cta_flags + (ti + 1) * fw + (tj + 1), epoch);
-            }
             if (threadIdx.x < 9 && threadIdx.x != 4) {
                 const int sy = (int)threadIdx.x / 3 - 1, sx = (int)threadIdx.x % 3 - 1;
                 const bool on_y = sy == 0 || (sy < 0 ? ti == 0 : ti == A.nty - 1);
                 const bool on_x = sx == 0 || (sx < 0 ? tj == 0 : tj == A.ntx - 1);
                 uint32_t* remote = A.remote_cta_flags[threadIdx.x];
-                if (on_y && on_x && remote != nullptr) {
-                    __threadfence_system();
+                if (on_y && on_x && remote != nullptr)
                     st_release_sys(remote + (ti + 1 - sy * A.nty) * fw + (tj + 1 - sx * A.ntx), epoch);
-                }
             }
             // 3. wait for the eight surrounding CTAs (local, or ring entries written by a neighbour GPU)
             if (threadIdx.x >= 32 && threadIdx.x < 41 && threadIdx.x != 36) {
@@ -189,13 +187,12 @@ resident_kernel(const __grid_constant__ ResidentArgs A) {
     // ---- launch-level protocol: publish "run done" -------------------------------------------------
     if (A.sync.signal_value != 0u) {
         __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();   // gpu scope; the last CTA's system fence below is cumulative
+        if (threadIdx.x == 0) {   // acq_rel ticket: releases this CTA's stores, acquires the others'
             const uint32_t ticket = atom_add_acq_rel_gpu(A.sync.done_counter, 1u);
             if (ticket == gridDim.x - 1) {
                 *A.sync.done_counter = 0u;
                 if (!A.sync.inject_drop_signal) {
-                    __threadfence_system();
+                    fence_acq_rel_sys();
 #pragma unroll
                     for (int d = 0; d < 9; ++d)
                         if (d != 4 && A.sync.remote_flags[d] != nullptr)

@@ -119,8 +119,7 @@ stream_kernel(const __grid_constant__ StreamArgs A) {
     // ---- halo protocol: publish "launch done" to the neighbours -----------------------------------
     if (A.sync.signal_value != 0u) {
         __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();   // gpu scope; the last CTA's system fence below is cumulative
+        if (threadIdx.x == 0) {   // acq_rel ticket: releases this CTA's stores, acquires the others'
             const uint32_t ticket = atom_add_acq_rel_gpu(A.sync.done_counter, 1u);
             if (ticket == gridDim.x - 1) {
                 *A.sync.done_counter = 0u;  // self-reset for the next launch (stream ordered)
@@ -129,7 +128,7 @@ stream_kernel(const __grid_constant__ StreamArgs A) {
                     while (globaltimer_ns() - t0 < (uint64_t)A.sync.inject_delay_ns) __nanosleep(256);
                 }
                 if (!A.sync.inject_drop_signal) {
-                    __threadfence_system();
+                    fence_acq_rel_sys();
 #pragma unroll
                     for (int d = 0; d < 9; ++d)
                         if (d != 4 && A.sync.remote_flags[d] != nullptr)

@@ -353,6 +353,58 @@ class ConvEngine:
         self.iterate(loops)
         return self.gather()
 
+    def run_batch(self, paths_in: list[str], loops: int, out_dir: str | None = None) -> dict:
+        """Data-parallel-in-time batch mode: filter many images of the engine's shape.
+
+        On the fused backend the images stream through the rotating buffer slots — the file read
+        and H2D copy of image i+1 and the D2H copy and file write of image i-1 overlap the
+        iterations of image i (``slots >= 2``). Other backends process the list sequentially.
+        Outputs are ``blur_<basename>`` in ``out_dir`` (default: next to each input). The
+        reference handles exactly one image per program run (SURVEY.md §2.6 "DP: No").
+        """
+        import time as _time
+        g, C = self.grid, self.grid.channels
+        t0 = _time.perf_counter()
+
+        def out_path(p: str) -> str:
+            d, b = os.path.split(p)
+            return os.path.join(out_dir if out_dir is not None else d, "blur_" + b)
+
+        pipelined = self.backend == "fused" and getattr(self._impl, "slots", 1) >= 2 and loops > 0
+        if not pipelined:
+            for p in paths_in:
+                self.run_file(p, loops, out_path(p))
+            return {"images": len(paths_in), "seconds": _time.perf_counter() - t0, "pipelined": False}
+        slots = self._impl.slots
+        stage = [self.pinned_buffers() for _ in range(slots)]
+        pending: list[tuple[int, str]] = []      # (slot, output path) in submission order
+
+        def flush(slot: int, path: str) -> None:
+            if self.rank == 0:
+                H.create_file(path, g.height * g.row_bytes)
+            if self.distributed:
+                self.dist.barrier()
+            for r, tile in stage[slot][1].items():
+                t = g.tile(r)
+                H.write_rect(path, g.row_bytes, t.row0, t.col0 * C, tile)
+
+        for i, p in enumerate(paths_in):
+            slot = i % slots
+            if len(pending) >= slots:            # the slot's previous result must leave before reuse
+                self.synchronize()
+                while pending:
+                    flush(*pending.pop(0))
+            ins, outs = stage[slot]
+            for r, arr in ins.items():
+                t = g.tile(r)
+                H.read_rect(p, g.row_bytes, t.row0, t.rows, t.col0 * C, t.cols * C, out=arr)
+            self.enqueue_step_pipelined(ins, outs, loops)
+            pending.append((slot, out_path(p)))
+        self.synchronize()
+        while pending:
+            flush(*pending.pop(0))
+        return {"images": len(paths_in), "seconds": _time.perf_counter() - t0, "pipelined": True}
+
     def run_file(self, path_in: str, loops: int, path_out: str | None = None) -> RunReport:
         """``prog image width height loops {rgb|grey}``: read, iterate, write ``blur_<image>``.
 

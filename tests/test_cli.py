@@ -76,3 +76,24 @@ def test_checkpoint_and_resume_are_bit_identical(raw, tmp_path):
     assert r.returncode == 0, r.stderr
     assert np.array_equal(np.fromfile(part, dtype=np.uint8), np.fromfile(full, dtype=np.uint8))
     assert not os.path.exists(str(part) + ".ckpt.json")    # cleaned up after a complete run
+
+
+def test_batch_mode_cpu(tmp_path):
+    rng = np.random.default_rng(2)
+    paths = []
+    for i in range(3):
+        img = rng.integers(0, 256, (24, 32, 3), dtype=np.uint8)
+        p = tmp_path / f"im{i}.raw"
+        img.tofile(p)
+        paths.append((p, img))
+    lst = tmp_path / "list.txt"
+    lst.write_text("\n".join(str(p) for p, _ in paths) + "\n")
+    outd = tmp_path / "out"
+    outd.mkdir()
+    r = run_cli("ignored", 32, 24, 4, "rgb", "--backend", "cpu", "--batch", lst, "-o", outd, "--json")
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout)["images"] == 3
+    f = Filter.builtin("gaussian")
+    for p, img in paths:
+        got = np.fromfile(outd / ("blur_" + p.name), dtype=np.uint8).reshape(img.shape)
+        assert np.array_equal(got, host.oracle(img, f.spec, 4))

@@ -52,3 +52,22 @@ def test_autotune_keeps_results_exact(rng, workers):
         assert info and info["mode"] in ("stream", "resident") and len(info["tried"]) >= 2
         out = eng.run(img, 20)
     assert np.array_equal(out, host.cpu_run_image(img, f.spec, 20))
+
+
+def test_batch_mode_streams_files(rng, tmp_path):
+    from parallel_convolution_b200 import ConvEngine
+    H, W, C, loops = 120, 160, 3, 6
+    f = Filter.builtin("sharpen")
+    paths, imgs = [], []
+    for i in range(5):
+        img = random_image(rng, H, W, C)
+        p = tmp_path / f"b{i}.raw"
+        img.tofile(p)
+        paths.append(str(p))
+        imgs.append(img)
+    with ConvEngine(width=W, height=H, channels=C, filter=f, backend="fused", workers=2, slots=3) as eng:
+        info = eng.run_batch(paths, loops, str(tmp_path))
+    assert info["pipelined"] and info["images"] == 5
+    for p, img in zip(paths, imgs):
+        got = np.fromfile(tmp_path / ("blur_" + p.split("/")[-1]), dtype=np.uint8).reshape(img.shape)
+        assert np.array_equal(got, host.cpu_run_image(img, f.spec, loops))
