@@ -103,6 +103,8 @@ void make_filter_dev(const pconv_filter_t& f, pconv::FilterDev* out) {
         if (f.w[i] > 0) ipos += f.w[i]; else ineg -= f.w[i];
     }
     out->shift = f.shift;
+    out->symmetric = f.h[0] == f.h[2] && f.h[3] == f.h[5] && f.h[6] == f.h[8] &&   // left == right
+                     f.h[0] == f.h[6] && f.h[1] == f.h[7];                             // top == bottom
     if (f.kind == PCONV_KIND_F32) {
         out->clamp_lo = neg > 0.0;
         out->clamp_hi = pos * 255.0 >= 255.5;  // below 256 truncation already yields <= 255

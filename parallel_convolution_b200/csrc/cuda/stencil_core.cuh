@@ -45,6 +45,7 @@ struct FilterDev {
     uint32_t maxv2;     // IntPath: packed ((256 << shift) - 1)
     int32_t clamp_lo;   // result can go negative  -> clamp at 0
     int32_t clamp_hi;   // result can exceed 255   -> clamp at 255
+    int32_t symmetric;  // F32Path: taps symmetric in both axes -> shared products (taps_symmetric)
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
@@ -170,19 +171,21 @@ struct IntPath {
                        wr = (uint32_t)f.w[3 * K + 2];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            uint32_t lE, rE, lO, rO;  // lanes at x-C / x+C for the even / odd positions of word j
-            if (C == 1) {
-                lE = lanes_shift(O[j], O[j + 1]); rE = O[j + 1];
-                lO = E[j + 1];                    rO = lanes_shift(E[j + 1], E[j + 2]);
-            } else {
-                lE = O[j];                        rE = lanes_shift(O[j + 1], O[j + 2]);
-                lO = lanes_shift(E[j], E[j + 1]); rO = E[j + 2];
-            }
             uint32_t e = fresh ? f.bias2 : accE[j];
             uint32_t o = fresh ? f.bias2 : accO[j];
-            if (wl) { e += wl * lE; o += wl * lO; }
+            // lanes at x-C / x+C for the even / odd positions of word j; the lane shifts are only
+            // built for taps that are not zero (warp-uniform branches on constant-bank weights)
+            if (wl) {
+                const uint32_t lE = C == 1 ? lanes_shift(O[j], O[j + 1]) : O[j];
+                const uint32_t lO = C == 1 ? E[j + 1] : lanes_shift(E[j], E[j + 1]);
+                e += wl * lE; o += wl * lO;
+            }
             if (wc) { e += wc * E[j + 1]; o += wc * O[j + 1]; }
-            if (wr) { e += wr * rE; o += wr * rO; }
+            if (wr) {
+                const uint32_t rE = C == 1 ? O[j + 1] : lanes_shift(O[j + 1], O[j + 2]);
+                const uint32_t rO = C == 1 ? lanes_shift(E[j + 1], E[j + 2]) : E[j + 2];
+                e += wr * rE; o += wr * rO;
+            }
             accE[j] = e; accO[j] = o;
         }
     }
@@ -293,13 +296,58 @@ struct F32Path {
         tap_row<1>(acc[(PH + 1) % 3], v, false);
         tap_row<0>(acc[(PH + 2) % 3], v, true);
     }
+    // Filters symmetric in both axes (box, the reference's "edge"/28, gaussian_soft, any isotropic
+    // kernel): taps (0,*) and (2,*) multiply the same pixels by the same weights, and so do the left
+    // and right tap of a row, so each product is computed once and added where the oracle adds it —
+    // same operands, same order, same roundings: 88 instead of 144 multiplies per 16 bytes.
+    template <int PH>
+    __device__ __forceinline__ void taps_symmetric(const float (&v)[16 + 2 * C]) {
+        const float hAs = f.h[0], hAc = f.h[1], hBs = f.h[3], hBc = f.h[4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int b0 = 8 * half;
+            {
+                float t[8 + 2 * C], c[8];
+#pragma unroll
+                for (int i = 0; i < 8 + 2 * C; ++i) t[i] = __fmul_rn(v[b0 + i], hAs);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) c[i] = __fmul_rn(v[b0 + i + C], hAc);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float a = __fadd_rn(acc[PH][b0 + i], t[i]);                  // taps (2,0) (2,1) (2,2)
+                    a = __fadd_rn(a, c[i]);
+                    acc[PH][b0 + i] = __fadd_rn(a, t[i + 2 * C]);
+                    const float z = __fadd_rn(t[i], c[i]);                       // taps (0,0) (0,1) (0,2), fresh
+                    acc[(PH + 2) % 3][b0 + i] = __fadd_rn(z, t[i + 2 * C]);
+                }
+            }
+            {
+                float t[8 + 2 * C], c[8];
+#pragma unroll
+                for (int i = 0; i < 8 + 2 * C; ++i) t[i] = __fmul_rn(v[b0 + i], hBs);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) c[i] = __fmul_rn(v[b0 + i + C], hBc);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float a = __fadd_rn(acc[(PH + 1) % 3][b0 + i], t[i]);        // taps (1,0) (1,1) (1,2)
+                    a = __fadd_rn(a, c[i]);
+                    acc[(PH + 1) % 3][b0 + i] = __fadd_rn(a, t[i + 2 * C]);
+                }
+            }
+        }
+    }
+
     template <int PH>
     __device__ __forceinline__ uint4 push(const uint4& w) {
         float v[16 + 2 * C];
         convert(w, v);
-        tap_row<2>(acc[PH], v, false);
-        tap_row<1>(acc[(PH + 1) % 3], v, false);
-        tap_row<0>(acc[(PH + 2) % 3], v, true);
+        if (f.symmetric) {
+            taps_symmetric<PH>(v);
+        } else {
+            tap_row<2>(acc[PH], v, false);
+            tap_row<1>(acc[(PH + 1) % 3], v, false);
+            tap_row<0>(acc[(PH + 2) % 3], v, true);
+        }
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
