@@ -103,7 +103,18 @@ class ConvEngine:
             raise ValueError(f"unknown backend {want!r}")
         if want == "auto":
             from .ops import cuda as K
-            return "fused" if K.available() else "cpu"
+            if K.available():
+                return "fused"
+            if os.path.exists("/dev/nvidiactl") and os.environ.get("PCONV_ALLOW_CPU_FALLBACK") != "1":
+                # a GPU box must never silently run the CPU engine: say why the CUDA path is unusable
+                try:
+                    K.lib()
+                    why = "libpconv_cuda.so loaded but reports no usable device"
+                except Exception as e:  # noqa: BLE001
+                    why = f"libpconv_cuda.so could not be built/loaded: {e}"
+                raise RuntimeError(f"NVIDIA driver present but the fused backend is unavailable ({why}); "
+                                   "pass --backend cpu (or PCONV_ALLOW_CPU_FALLBACK=1) to run on the CPU")
+            return "cpu"
         if want in ("fused", "nccl"):
             from .ops import cuda as K
             if not K.available():
