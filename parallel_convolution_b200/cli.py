@@ -72,15 +72,18 @@ def _init_dist(backend: str):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world <= 1:
         return None
+    import datetime
     import torch
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    # a rank that dies (bad file, watchdog) must not leave the others in a collective for 10 minutes
+    limit = datetime.timedelta(seconds=int(os.environ.get("PCONV_DIST_TIMEOUT_S", "180")))
     if backend in ("cpu", "host") or not torch.cuda.is_available():
-        dist.init_process_group("gloo")
+        dist.init_process_group("gloo", timeout=limit)
     else:
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=limit)
     return dist
 
 
