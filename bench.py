@@ -239,13 +239,14 @@ def run_reference(a) -> dict:
     try:
         for _ in range(max(1, min(a.warmup, 2))):
             once(LOOPS)                        # JIT of the compute_52 PTX + page-in
-        reps = max(1, min(a.steps, 5))
-        t100 = min(once(LOOPS) for _ in range(reps))
-        t20 = min(once(20) for _ in range(reps))
+        reps = max(2, min(a.steps, 4))
+        long_loops = LOOPS + 1000                 # a long run isolates the per-iteration cost from the
+        t100 = min(once(LOOPS) for _ in range(reps))          # ~1.3 s of start-up, file I/O and JIT
+        tlong = min(once(long_loops) for _ in range(reps))
     except Exception as e:  # noqa: BLE001
         return {"impl": "reference", "unavailable": f"reference cuda_conv failed to run: {e}"}
     px = WIDTH * HEIGHT
-    marginal_s = max((t100 - t20) / 80.0, 1e-9)       # per-iteration device cost, I/O and startup removed
+    marginal_s = max((tlong - t100) / (long_loops - LOOPS), 1e-9)   # per-iteration device cost only
     value = px / marginal_s / 1e6
     whole = px * LOOPS / t100 / 1e6
     return {"metric": METRIC, "value": round(value, 1), "unit": "Mpx/s", "n_gpus": 1, "steps": reps,
@@ -258,8 +259,10 @@ def run_reference(a) -> dict:
                        "iterations_per_step": LOOPS, "binary": "baseline/_ref/cuda/cuda_conv (unmodified sources, "
                        "its own Makefile: sm_52 SASS + compute_52 PTX, JIT on B200)",
                        "timing": "value = marginal loop rate from the reference's own host timer "
-                                 "((t(100 it) - t(20 it)) / 80); e2e = its whole-program time incl. file I/O"},
-            "e2e": {"value": round(whole, 1), "unit": "Mpx/s", "seconds_100_iters": t100, "seconds_20_iters": t20},
+                                 "((t(1100 it) - t(100 it)) / 1000, best of N runs each); e2e = its "
+                                 "whole-program time for 100 iterations incl. file I/O"},
+            "e2e": {"value": round(whole, 1), "unit": "Mpx/s", "seconds_100_iters": t100,
+                    "seconds_1100_iters": tlong},
             "gpu_launches": LOOPS}
 
 
