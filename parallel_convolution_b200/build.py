@@ -57,11 +57,27 @@ def _run(cmd: list[str], log: Path | None = None) -> None:
         raise RuntimeError(f"build step failed ({proc.returncode}): {' '.join(cmd)}")
 
 
-def _stale(target: Path, sources: list[Path]) -> bool:
-    if not target.exists():
+def _digest(sources: list[Path], flags: list[str]) -> str:
+    """Content hash of a target's inputs. File times are useless here: the tree is snapshotted onto
+    fresh GPU boxes and checked out by the driver, which rewrites every mtime."""
+    import hashlib
+    h = hashlib.sha256(" ".join(flags).encode())
+    for s in sorted(set(sources), key=lambda q: str(q)):
+        if s.exists():
+            h.update(str(s.relative_to(PKG)).encode())
+            h.update(s.read_bytes())
+    return h.hexdigest()
+
+
+def _stale(target: Path, sources: list[Path], flags: list[str] | None = None) -> bool:
+    stamp = target.with_name(target.name + ".hash")
+    if not target.exists() or not stamp.exists():
         return True
-    t = target.stat().st_mtime
-    return any(s.stat().st_mtime > t for s in sources if s.exists())
+    return stamp.read_text().strip() != _digest(sources, flags or [])
+
+
+def _stamp(target: Path, sources: list[Path], flags: list[str] | None = None) -> None:
+    target.with_name(target.name + ".hash").write_text(_digest(sources, flags or []))
 
 
 def _all_headers() -> list[Path]:
@@ -71,7 +87,7 @@ def _all_headers() -> list[Path]:
 def build_host(force: bool = False) -> Path:
     LIB.mkdir(exist_ok=True)
     srcs = [CSRC / s for s in HOST_SOURCES] + [CSRC / HOST_ORACLE]
-    if not force and not _stale(HOST_LIB, srcs + _all_headers()):
+    if not force and not _stale(HOST_LIB, srcs + _all_headers(), CXXFLAGS):
         return HOST_LIB
     objs = []
     for s in HOST_SOURCES:
@@ -83,6 +99,7 @@ def build_host(force: bool = False) -> Path:
           "-c", str(CSRC / HOST_ORACLE), "-o", str(o)])
     objs.append(str(o))
     _run([CXX, "-shared", "-fopenmp", "-o", str(HOST_LIB), *objs])
+    _stamp(HOST_LIB, srcs + _all_headers(), CXXFLAGS)
     return HOST_LIB
 
 
@@ -100,7 +117,7 @@ def build_host_sanitized() -> Path:
 def build_cuda(force: bool = False) -> Path:
     LIB.mkdir(exist_ok=True)
     srcs = [CSRC / s for s in CUDA_SOURCES if (CSRC / s).exists()]
-    if not force and not _stale(CUDA_LIB, srcs + _all_headers()):
+    if not force and not _stale(CUDA_LIB, srcs + _all_headers(), NVCCFLAGS):
         return CUDA_LIB
     if not Path(NVCC).exists():
         raise RuntimeError(f"nvcc not found at {NVCC}; the CUDA library cannot be built")
@@ -109,14 +126,16 @@ def build_cuda(force: bool = False) -> Path:
 
     def compile_one(s: Path) -> str:
         o = LIB / (s.stem + ".cu.o")
-        if force or _stale(o, [s] + hdrs):
+        if force or _stale(o, [s] + hdrs, NVCCFLAGS):
             _run([NVCC, *NVCCFLAGS, "-c", str(s), "-o", str(o)], log=LIB / (s.stem + ".ptxas.log"))
+            _stamp(o, [s] + hdrs, NVCCFLAGS)
         return str(o)
 
     with ThreadPoolExecutor(max_workers=min(4, len(srcs))) as ex:   # the kernel TUs take minutes
         objs = list(ex.map(compile_one, srcs))
     _run([NVCC, "-ccbin", CXX, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(CUDA_LIB),
           *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    _stamp(CUDA_LIB, srcs + _all_headers(), NVCCFLAGS)
     return CUDA_LIB
 
 
@@ -127,10 +146,12 @@ def build_native(force: bool = False) -> Path | None:
         return None
     build_host(force)
     build_cuda(force)
-    if not force and not _stale(NATIVE_BIN, [main, HOST_LIB, CUDA_LIB]):
+    nsrc = [main] + _all_headers()
+    if not force and NATIVE_BIN.exists() and not _stale(NATIVE_BIN, nsrc):
         return NATIVE_BIN
     _run([CXX, "-std=c++17", "-O2", f"-I{CSRC}", str(main), "-o", str(NATIVE_BIN), f"-L{LIB}",
           "-lpconv_host", "-lpconv_cuda", "-Wl,-rpath,$ORIGIN", "-fopenmp"])
+    _stamp(NATIVE_BIN, nsrc)
     return NATIVE_BIN
 
 
