@@ -141,3 +141,14 @@ def test_native_planner_invariants():
     r = plan_resident(2520, 5760, 3, 2, 100)
     assert r is not None and r.ntx * r.nty <= 148 and r.TH >= r.k
     assert plan_resident(16384, 16384, 1, 2, 100) is None      # does not fit on chip -> stream
+
+
+@pytest.mark.parametrize("name", ["gaussian", "box", "edge", "sharpen", "sobel_x"])
+def test_cpu_engine_matches_plain_torch_fp32(rng, name):
+    """Same plain-PyTorch fp32 reference the GPU tests use (tests/test_gpu_vs_torch.py)."""
+    from test_gpu_vs_torch import torch_reference
+    img = random_image(rng, 33, 47, 3)
+    f = Filter.builtin(name)
+    ref = torch_reference(img, f.taps, 3, "cpu")
+    assert np.array_equal(host.cpu_run_image(img, f.spec, 3), ref)
+    assert np.array_equal(host.oracle(img, f.spec, 3), ref)
