@@ -39,8 +39,9 @@ CXX = _pick_cxx()
 HOST_SOURCES = ["host/filters.cpp", "host/decomp.cpp", "host/cpu_engine.cpp", "host/rawio.cpp",
                 "host/planner.cpp"]
 HOST_ORACLE = "host/oracle.cpp"  # compiled separately at -O1 with contraction off
-CUDA_SOURCES = ["cuda/runtime.cu", "cuda/stream_kernel.cu", "cuda/resident_kernel.cu",
-                "cuda/pack_kernels.cu"]
+CUDA_SOURCES = ["cuda/runtime.cu", "cuda/pack_kernels.cu", "cuda/stream_kernel.cu", "cuda/resident_kernel.cu",
+                "cuda/stream_kind_sep.cu", "cuda/stream_kind_int.cu", "cuda/stream_kind_f32.cu",
+                "cuda/resident_kind_sep.cu", "cuda/resident_kind_int.cu", "cuda/resident_kind_f32.cu"]
 
 CXXFLAGS = ["-std=c++17", "-fPIC", "-O3", "-ffp-contract=off", "-fopenmp", "-Wall",
             "-Wno-unknown-pragmas"]
@@ -131,7 +132,7 @@ def build_cuda(force: bool = False) -> Path:
             _stamp(o, [s] + hdrs, NVCCFLAGS)
         return str(o)
 
-    with ThreadPoolExecutor(max_workers=min(4, len(srcs))) as ex:   # the kernel TUs take minutes
+    with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, len(srcs))) as ex:   # the kernel TUs take minutes
         objs = list(ex.map(compile_one, srcs))
     _run([NVCC, "-ccbin", CXX, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(CUDA_LIB),
           *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])

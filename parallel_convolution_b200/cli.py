@@ -35,7 +35,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("width", type=int)
     p.add_argument("height", type=int)
     p.add_argument("loops", type=int)
-    p.add_argument("color", choices=["rgb", "grey", "gray"])
+    p.add_argument("color", choices=["rgb", "grey", "gray", "rgba"],
+                   help="rgb / grey as in the reference; rgba (4 interleaved channels) is an extension")
     p.add_argument("--filter", default="gaussian",
                    help="builtin name (box, gaussian, edge, sharpen, laplacian, emboss, sobel_x, sobel_y, "
                         "identity), 'a,b,c,d,e,f,g,h,i[/div]', nine floats, or a file")
@@ -98,7 +99,7 @@ def main(argv: list[str] | None = None) -> int:
     if a.width <= 0 or a.height <= 0 or a.loops < 0:
         sys.stderr.write("width and height must be positive, loops non-negative\n")
         return 2
-    channels = 3 if a.color == "rgb" else 1
+    channels = {"rgb": 3, "rgba": 4}.get(a.color, 1)
     grid = tuple(int(v) for v in a.grid.lower().split("x")) if a.grid else None
     dist = _init_dist(a.backend)
     rank = dist.get_rank() if dist else 0

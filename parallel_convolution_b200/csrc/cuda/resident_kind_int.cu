@@ -1,0 +1,6 @@
+// Instantiates resident_kernel<PCONV_KIND_INT, C, R> for every compiled channel stride and band height.
+#include "resident_kernel.cuh"
+
+namespace pconv {
+ResidentFn pick_resident_int(int C, int R) { return pick_resident_kind<PCONV_KIND_INT>(C, R); }
+}  // namespace pconv

@@ -76,7 +76,7 @@ __device__ __forceinline__ uint32_t lanes_shift(uint32_t a, uint32_t b) { return
 // =============================================================================================
 template <int C>
 struct Sep121Path {
-    static_assert(C == 1 || C == 3, "channel strides 1 (grey) and 3 (RGB) are implemented");
+    static_assert(C == 1 || C == 3 || C == 4, "channel strides 1 (grey), 3 (RGB) and 4 (RGBA) are implemented");
     uint32_t uE[4], uO[4];  // unpacked lanes of the last pushed row
     uint32_t pE[4], pO[4];  // pair sum U_{r-1} + U_r
 
@@ -129,6 +129,16 @@ struct Sep121Path {
                 const uint32_t oO = 2u * vO[j] + vE[j] + lanes_shift(vE[j], eNext);
                 o[j] = prmt(oE << 4, oO << 4, 0x7351u);
             }
+        } else if (C == 4) {
+            // RGBA: x +- 4 is the same lane of the adjacent word — no lane shifts at all
+            const uint32_t eL = __shfl_up_sync(kFull, vE[3], 1), oL = __shfl_up_sync(kFull, vO[3], 1);
+            const uint32_t eR = __shfl_down_sync(kFull, vE[0], 1), oR = __shfl_down_sync(kFull, vO[0], 1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t oE = 2u * vE[j] + (j ? vE[j - 1] : eL) + (j < 3 ? vE[j + 1] : eR);
+                const uint32_t oO = 2u * vO[j] + (j ? vO[j - 1] : oL) + (j < 3 ? vO[j + 1] : oR);
+                o[j] = prmt(oE << 4, oO << 4, 0x7351u);
+            }
         } else {
             const uint32_t eL = __shfl_up_sync(kFull, vE[3], 1), oL = __shfl_up_sync(kFull, vO[3], 1);
             const uint32_t eR = __shfl_down_sync(kFull, vE[0], 1), oR = __shfl_down_sync(kFull, vO[0], 1);
@@ -156,7 +166,7 @@ struct Sep121Path {
 // =============================================================================================
 template <int C>
 struct IntPath {
-    static_assert(C == 1 || C == 3, "channel strides 1 (grey) and 3 (RGB) are implemented");
+    static_assert(C == 1 || C == 3 || C == 4, "channel strides 1 (grey), 3 (RGB) and 4 (RGBA) are implemented");
     uint32_t aE[3][4], aO[3][4];  // [slot][word]; slot roles rotate with the row phase
     const FilterDev& f;
 
@@ -176,14 +186,14 @@ struct IntPath {
             // lanes at x-C / x+C for the even / odd positions of word j; the lane shifts are only
             // built for taps that are not zero (warp-uniform branches on constant-bank weights)
             if (wl) {
-                const uint32_t lE = C == 1 ? lanes_shift(O[j], O[j + 1]) : O[j];
-                const uint32_t lO = C == 1 ? E[j + 1] : lanes_shift(E[j], E[j + 1]);
+                const uint32_t lE = C == 1 ? lanes_shift(O[j], O[j + 1]) : (C == 3 ? O[j] : E[j]);
+                const uint32_t lO = C == 1 ? E[j + 1] : (C == 3 ? lanes_shift(E[j], E[j + 1]) : O[j]);
                 e += wl * lE; o += wl * lO;
             }
             if (wc) { e += wc * E[j + 1]; o += wc * O[j + 1]; }
             if (wr) {
-                const uint32_t rE = C == 1 ? O[j + 1] : lanes_shift(O[j + 1], O[j + 2]);
-                const uint32_t rO = C == 1 ? lanes_shift(E[j + 1], E[j + 2]) : E[j + 2];
+                const uint32_t rE = C == 1 ? O[j + 1] : (C == 3 ? lanes_shift(O[j + 1], O[j + 2]) : E[j + 2]);
+                const uint32_t rO = C == 1 ? lanes_shift(E[j + 1], E[j + 2]) : (C == 3 ? E[j + 2] : O[j + 2]);
                 e += wr * rE; o += wr * rO;
             }
             accE[j] = e; accO[j] = o;
@@ -245,7 +255,7 @@ struct IntPath {
 // =============================================================================================
 template <int C>
 struct F32Path {
-    static_assert(C == 1 || C == 3, "channel strides 1 (grey) and 3 (RGB) are implemented");
+    static_assert(C == 1 || C == 3 || C == 4, "channel strides 1 (grey), 3 (RGB) and 4 (RGBA) are implemented");
     float acc[3][16];
     const FilterDev& f;
 

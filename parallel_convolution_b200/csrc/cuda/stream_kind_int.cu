@@ -1,0 +1,6 @@
+// Instantiates stream_kernel<PCONV_KIND_INT, C, R> for every compiled channel stride and band height.
+#include "stream_kernel.cuh"
+
+namespace pconv {
+KernelFn pick_stream_int(int C, int R) { return pick_stream_kind<PCONV_KIND_INT>(C, R); }
+}  // namespace pconv

@@ -18,11 +18,11 @@ OUT = os.path.join(ROOT, "profiles")
 os.makedirs(OUT, exist_ok=True)
 
 KERNELS = {
-    "stream_sep121_rgb_R14": ("stream_kernel.cu.o", "_ZN5pconv13stream_kernelILi2ELi3ELi14EEEvNS_10StreamArgsE"),
-    "stream_sep121_grey_R14": ("stream_kernel.cu.o", "_ZN5pconv13stream_kernelILi2ELi1ELi14EEEvNS_10StreamArgsE"),
-    "stream_int_rgb_R10": ("stream_kernel.cu.o", "_ZN5pconv13stream_kernelILi1ELi3ELi10EEEvNS_10StreamArgsE"),
-    "stream_f32_grey_R8": ("stream_kernel.cu.o", "_ZN5pconv13stream_kernelILi0ELi1ELi8EEEvNS_10StreamArgsE"),
-    "resident_sep121_rgb_R14": ("resident_kernel.cu.o", "_ZN5pconv15resident_kernelILi2ELi3ELi14EEEvNS_12ResidentArgsE"),
+    "stream_sep121_rgb_R14": ("stream_kind_sep.cu.o", "_ZN5pconv13stream_kernelILi2ELi3ELi14EEEvNS_10StreamArgsE"),
+    "stream_sep121_grey_R14": ("stream_kind_sep.cu.o", "_ZN5pconv13stream_kernelILi2ELi1ELi14EEEvNS_10StreamArgsE"),
+    "stream_int_rgb_R10": ("stream_kind_int.cu.o", "_ZN5pconv13stream_kernelILi1ELi3ELi10EEEvNS_10StreamArgsE"),
+    "stream_f32_grey_R8": ("stream_kind_f32.cu.o", "_ZN5pconv13stream_kernelILi0ELi1ELi8EEEvNS_10StreamArgsE"),
+    "resident_sep121_rgb_R14": ("resident_kind_sep.cu.o", "_ZN5pconv15resident_kernelILi2ELi3ELi14EEEvNS_12ResidentArgsE"),
 }
 
 

@@ -113,6 +113,16 @@ def test_reference_image_config(rng):
     assert np.array_equal(_run(img, f, 12, workers=8), ref)
 
 
+@pytest.mark.parametrize("name", ["gaussian", "sharpen", "box"])
+def test_rgba_four_channel_images(rng, name):
+    """Channel stride 4 (RGBA): an extension over the reference's grey / rgb."""
+    img = random_image(rng, 120, 200, 4)
+    f = Filter.builtin(name)
+    ref = host.oracle(img, f.spec, 5)
+    assert np.array_equal(_run(img, f, 5), ref)
+    assert np.array_equal(_run(img, f, 5, workers=4), ref)
+
+
 def test_device_synth_matches_host():
     from parallel_convolution_b200.parallel.decomposition import TileGrid
     from parallel_convolution_b200.parallel.fused import VirtualCluster
