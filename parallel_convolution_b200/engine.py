@@ -147,7 +147,15 @@ class ConvEngine:
 
     def close(self) -> None:
         if self._impl is not None and hasattr(self._impl, "close"):
-            self._impl.close()
+            self._impl.close()          # synchronises every stream first
+        if self.backend != "cpu" and self._impl is not None:
+            from .ops import cuda as K
+            for bufs in getattr(self, "_pool", []):
+                for p in bufs.values():
+                    K.free(p)
+            for p in getattr(self, "_pinned", []):
+                K.host_free(p)
+            self._pool, self._pinned = [], []
         self._impl = None
 
     def __enter__(self):
@@ -324,6 +332,7 @@ class ConvEngine:
             n = t.rows * t.cols * C
             for table in (ins, outs):
                 p = K.host_alloc(n)
+                self.__dict__.setdefault("_pinned", []).append(p)
                 arr = np.ctypeslib.as_array((ctypes.c_uint8 * n).from_address(p)).reshape(t.rows, t.cols * C)
                 table[r] = arr
         return ins, outs
