@@ -63,6 +63,10 @@ int pconv_cpu_convolve(const uint8_t* src0, uint8_t* dst0, int64_t pitch, int C,
 // Whole dense image, `loops` iterations, zero padded, multi-threaded; dst receives the result.
 int pconv_cpu_run_image(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
                         const pconv_filter_t* f, int loops, int threads);
+// Same result, temporally blocked: row bands advance k iterations in L2-sized private buffers
+// (pconv_cpu_run_image picks this automatically for memory-bound sizes).
+int pconv_cpu_run_image_blocked(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
+                                const pconv_filter_t* f, int loops, int threads, int k);
 int pconv_omp_max_threads(void);
 
 // ---- raw image I/O (64-bit offsets; reference: MPI_File_* mpi/mpi_conv.c:133-147,253-271) ----

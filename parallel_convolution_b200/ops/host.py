@@ -60,6 +60,7 @@ def lib() -> C.CDLL:
     L.pconv_oracle_run.argtypes = [u8p, u8p, u8p, i64, i64, C.c_int, fsp, C.c_int]
     L.pconv_cpu_convolve.argtypes = [u8p, u8p, i64, C.c_int, fsp, i64, i64, i64, i64, C.c_int]
     L.pconv_cpu_run_image.argtypes = [u8p, u8p, i64, i64, C.c_int, fsp, C.c_int, C.c_int]
+    L.pconv_cpu_run_image_blocked.argtypes = [u8p, u8p, i64, i64, C.c_int, fsp, C.c_int, C.c_int, C.c_int]
     L.pconv_file_size.argtypes = [C.c_char_p]
     L.pconv_file_size.restype = i64
     L.pconv_read_rect.argtypes = [C.c_char_p, i64, i64, i64, i64, i64, u8p, i64]
@@ -150,6 +151,18 @@ def cpu_run_image(image: np.ndarray, f: FilterSpec, loops: int, threads: int = 0
     rc = lib().pconv_cpu_run_image(_ptr(img), _ptr(out), H, W, Cn, C.byref(f), loops, threads)
     if rc != 0:
         raise RuntimeError(f"cpu engine failed ({rc})")
+    return out
+
+
+def cpu_run_image_blocked(image: np.ndarray, f: FilterSpec, loops: int, k: int, threads: int = 0) -> np.ndarray:
+    """Temporally blocked CPU run (k iterations per pass over memory); bit-identical to the oracle."""
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    H, W = img.shape[:2]
+    Cn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty_like(img)
+    rc = lib().pconv_cpu_run_image_blocked(_ptr(img), _ptr(out), H, W, Cn, C.byref(f), loops, threads, k)
+    if rc != 0:
+        raise RuntimeError(f"blocked cpu engine failed ({rc})")
     return out
 
 

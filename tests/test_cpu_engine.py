@@ -152,3 +152,12 @@ def test_cpu_engine_matches_plain_torch_fp32(rng, name):
     ref = torch_reference(img, f.taps, 3, "cpu")
     assert np.array_equal(host.cpu_run_image(img, f.spec, 3), ref)
     assert np.array_equal(host.oracle(img, f.spec, 3), ref)
+
+
+@pytest.mark.parametrize("k", [1, 3, 7])
+def test_cpu_temporal_blocking_is_bit_identical(rng, k):
+    img = random_image(rng, 150, 97, 3)
+    for name in ("gaussian", "edge", "laplacian"):
+        f = Filter.builtin(name)
+        assert np.array_equal(host.cpu_run_image_blocked(img, f.spec, 10, k, threads=3),
+                              host.oracle(img, f.spec, 10)), (name, k)
