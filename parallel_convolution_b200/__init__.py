@@ -2,7 +2,7 @@
 
 Capabilities of jimouris/parallel-convolution (MPI / MPI+OpenMP / CUDA programs applying a 3x3
 filter ``loops`` times to raw grey / interleaved-RGB images), rebuilt for one 8xB200 NVSwitch box:
-hand-written sm_100a kernels with temporal blocking in shared memory, halo exchange fused into
+hand-written sm_100a kernels with temporal blocking in registers, halo exchange fused into
 the stencil kernel through NVLink peer memory, a NCCL baseline, and a native CPU engine.
 
 Public API::

@@ -1,5 +1,5 @@
-// Global <-> shared-memory movement of CTA regions, owner lookup across the 3x3 tile
-// neighbourhood, and the system-scope flag primitives of the in-kernel halo protocol.
+// Global memory <-> register movement of CTA regions (band loads/stores), owner lookup across the
+// 3x3 tile neighbourhood, and the system-scope flag primitives of the in-kernel halo protocol.
 //
 // This is where the halo exchange is *fused* into the stencil kernel: a region row/column that
 // belongs to a neighbouring tile is loaded straight from that tile's buffer through its

@@ -31,7 +31,7 @@ namespace pconv {
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSP = 512;            // region width == smem row pitch, bytes
+constexpr int kSP = 512;            // region width in bytes (32 lanes x 16-byte strips)
 constexpr int kChunksPerRow = kSP / 16;  // 32 == one 16-byte chunk per lane
 constexpr unsigned kFull = 0xffffffffu;
 
