@@ -28,8 +28,9 @@ void classify(pconv_filter_t* f, bool integral, int shift) {
     }
     int64_t sum_abs = 0;
     for (int i = 0; i < 9; ++i) sum_abs += std::llabs((long long)f->w[i]);
-    // 16-bit SWAR lanes need (S_max - S_min) = sum|w|*255 <= 32767.
-    if (sum_abs > 128 || shift < 0 || shift > 8) return;
+    // 16-bit SWAR lanes need (S_max - S_min) = sum|w|*255 <= 32767, and the packed clamp constant
+    // (256 << shift) - 1 must fit a signed 16-bit lane: shift <= 7.
+    if (sum_abs > 128 || shift < 0 || shift > 7) return;
     f->shift = shift;
     f->kind = PCONV_KIND_INT;
     if (shift == 4 && std::memcmp(f->w, kGauss, sizeof(kGauss)) == 0) f->kind = PCONV_KIND_SEP121;
@@ -44,7 +45,7 @@ extern "C" int pconv_filter_from_int(const int32_t w[9], double div, pconv_filte
         out->h[i] = (float)((double)w[i] / div);  // int / double -> float, as the reference
     }
     int shift = -1;
-    for (int s = 0; s <= 8; ++s)
+    for (int s = 0; s <= 7; ++s)
         if (div == (double)(1 << s)) shift = s;
     classify(out, shift >= 0, shift);
     return 0;
@@ -54,7 +55,7 @@ extern "C" int pconv_filter_from_float(const float h[9], pconv_filter_t* out) {
     if (!out) return -1;
     for (int i = 0; i < 9; ++i) out->h[i] = h[i];
     // smallest s such that every tap * 2^s is an integer
-    for (int s = 0; s <= 8; ++s) {
+    for (int s = 0; s <= 7; ++s) {
         bool ok = true;
         for (int i = 0; i < 9 && ok; ++i) {
             float v = h[i] * (float)(1 << s);  // exact: power-of-two scaling

@@ -1,0 +1,75 @@
+"""Property-based tests (hypothesis) of the pure logic: decomposition, planner, filter
+classification, and the exactness claims the integer paths rest on."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from parallel_convolution_b200.models.filters import Filter
+from parallel_convolution_b200.ops import host
+from parallel_convolution_b200.parallel.decomposition import TileGrid
+from parallel_convolution_b200.parallel.plan import plan_resident, plan_stream
+
+
+@settings(max_examples=60, deadline=None)
+@given(h=st.integers(1, 400), w=st.integers(1, 400), n=st.integers(1, 16), c=st.sampled_from([1, 3, 4]))
+def test_tiles_partition_the_image(h, w, n, c):
+    try:
+        g = TileGrid.create(h, w, c, n)
+    except ValueError:
+        return                      # more workers than pixels along every factorisation
+    seen = np.zeros((h, w), dtype=np.int32)
+    for t in g.tiles():
+        assert t.rows >= 1 and t.cols >= 1
+        seen[t.row0:t.row0 + t.rows, t.col0:t.col0 + t.cols] += 1
+    assert (seen == 1).all()
+    rows = {t.rows for t in g.tiles()}
+    assert max(rows) - min(rows) <= 1           # balanced remainder split
+    if h % g.grid_rows == 0 and w % g.grid_cols == 0:
+        assert g.exact
+
+
+@settings(max_examples=60, deadline=None)
+@given(h=st.integers(2, 300), w=st.integers(2, 300), gr=st.integers(1, 4), gc=st.integers(1, 4))
+def test_neighbor_table_is_symmetric(h, w, gr, gc):
+    if gr > h or gc > w:
+        return
+    g = TileGrid.create(h, w, 1, gr * gc, (gr, gc))
+    for r in range(g.workers):
+        for d, nb in enumerate(g.neighbors(r)):
+            if nb >= 0:
+                assert g.neighbors(nb)[8 - d] == r      # I am my neighbour's opposite neighbour
+
+
+@settings(max_examples=80, deadline=None)
+@given(rows=st.integers(1, 40000), cb=st.integers(1, 120000), c=st.sampled_from([1, 3, 4]),
+       kind=st.sampled_from([0, 1, 2]), loops=st.integers(1, 600))
+def test_stream_plans_are_always_launchable(rows, cb, c, kind, loops):
+    p = plan_stream(rows, cb * c, c, kind, loops)
+    assert 1 <= p.k <= loops
+    assert p.TH >= 1 and p.TH + 2 * p.k <= 16 * p.R
+    assert p.HB % 16 == 0 and p.HB >= p.k * c and p.TWB + 2 * p.HB == 512
+    assert p.ntx * p.TWB >= cb * c and p.nty * p.TH >= rows
+    assert sum(p.launches(loops)) == loops and all(1 <= k <= p.k for k in p.launches(loops))
+    r = plan_resident(rows, cb * c, c, kind, loops)
+    if r is not None:
+        assert r.ntx * r.nty <= 148 and r.TH >= r.k and r.TWB >= r.HB
+
+
+@settings(max_examples=40, deadline=None)
+@given(w=st.lists(st.integers(-14, 14), min_size=9, max_size=9), s=st.integers(0, 7),
+       seed=st.integers(0, 2**31 - 1))
+def test_integer_filters_are_exact_in_fp32(w, s, seed):
+    """The classifier's claim: integer taps over 2^s (sum|w| <= 128) => the fp32 oracle equals
+    clamp(floor(S / 2^s), 0, 255) for every input."""
+    f = Filter.from_int(w, float(1 << s))
+    if f.kind_name == "f32-exact":
+        assert sum(abs(v) for v in w) > 128
+        return
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (12, 14), dtype=np.uint8)
+    p = np.zeros((14, 16), dtype=np.int64)
+    p[1:-1, 1:-1] = img
+    wm = np.array(w).reshape(3, 3)
+    S = sum(wm[k, l] * p[k:k + 12, l:l + 14] for k in range(3) for l in range(3))
+    want = np.clip(S >> s, 0, 255).astype(np.uint8)
+    assert np.array_equal(host.oracle(img, f.spec, 1), want)
+    assert np.array_equal(host.cpu_run_image(img, f.spec, 1), want)
