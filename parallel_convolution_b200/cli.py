@@ -45,6 +45,9 @@ def build_parser() -> argparse.ArgumentParser:
                    help="fused backend: persistent on-chip kernel vs streaming launches")
     p.add_argument("--gpus", "--workers", dest="workers", type=int, default=None,
                    help="single process: decompose over N virtual ranks on one GPU")
+    p.add_argument("-np", "--np", dest="nprocs", type=int, default=None, metavar="N",
+                   help="spawn N ranks on this node (one per GPU, or CPU ranks with --backend cpu): the "
+                        "reference's `mpirun -np N`; equivalent to launching this module under torchrun")
     p.add_argument("--grid", default=None, help="tile grid ROWSxCOLS (default: perimeter-minimising)")
     p.add_argument("--halo-depth", type=int, default=None, help="temporal-blocking depth k")
     p.add_argument("--autotune", action="store_true",
@@ -88,8 +91,29 @@ def _init_dist(backend: str):
     return dist
 
 
+def _spawn_ranks(nprocs: int, argv: list[str]) -> int:
+    """``pconv -np N ...``: re-launch this command as N ranks under ``torch.distributed.run``.
+
+    The reference is started as ``mpirun -np N ./mpi_conv ...`` (``mpi/READ_ME.txt:5``); here the launcher
+    is torchrun with a loopback rendezvous, so the whole thing stays one command."""
+    import subprocess
+    rest, skip = [], False
+    for tok in argv:
+        if skip:
+            skip = False
+        elif tok in ("-np", "--np"):
+            skip = True
+        elif not tok.startswith(("--np=", "-np=")):
+            rest.append(tok)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--standalone", "--local-addr", "127.0.0.1",
+           "--nnodes", "1", "--nproc-per-node", str(nprocs), "-m", __package__] + rest
+    return subprocess.call(cmd)
+
+
 def main(argv: list[str] | None = None) -> int:
     parser = build_parser()
+    if argv is None:
+        argv = sys.argv[1:]
     try:
         a = parser.parse_args(argv)
     except SystemExit as e:
@@ -99,6 +123,12 @@ def main(argv: list[str] | None = None) -> int:
     if a.width <= 0 or a.height <= 0 or a.loops < 0:
         sys.stderr.write("width and height must be positive, loops non-negative\n")
         return 2
+    if a.nprocs is not None and int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        if a.nprocs < 1:
+            sys.stderr.write("-np needs a positive rank count\n")
+            return 2
+        if a.nprocs > 1:
+            return _spawn_ranks(a.nprocs, list(argv))
     channels = {"rgb": 3, "rgba": 4}.get(a.color, 1)
     grid = tuple(int(v) for v in a.grid.lower().split("x")) if a.grid else None
     dist = _init_dist(a.backend)

@@ -97,3 +97,14 @@ def test_batch_mode_cpu(tmp_path):
     for p, img in paths:
         got = np.fromfile(outd / ("blur_" + p.name), dtype=np.uint8).reshape(img.shape)
         assert np.array_equal(got, host.oracle(img, f.spec, 4))
+
+
+def test_np_flag_spawns_ranks_like_mpirun(raw):
+    """`pconv -np 2 ...` == `mpirun -np 2 ./mpi_conv ...`: two gloo ranks, one output, oracle bytes."""
+    p, img = raw
+    r = run_cli("-np", 2, p, 56, 40, 5, "grey", "--backend", "cpu", "--json")
+    assert r.returncode == 0, r.stderr
+    rep = json.loads(r.stdout.strip().splitlines()[-1])
+    assert rep["workers"] == 2
+    got = np.fromfile(p.parent / ("blur_" + p.name), dtype=np.uint8).reshape(40, 56)
+    assert np.array_equal(got, host.oracle(img, Filter.builtin("gaussian").spec, 5))
