@@ -16,6 +16,8 @@ backends, and for CPU-only boxes. World size 1 needs no process group at all.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from ..models.filters import Filter
@@ -40,6 +42,11 @@ class HostTile:
         self.cur = 0
         self.nbrs = grid.neighbors(rank)
         self.exchanges = 0
+        # Debug aid: overwrite every halo that has a neighbour with 0xA5 right before
+        # each exchange, so a strip that is consumed without having been freshly received (a missing
+        # diagonal, a wrong tag, a skipped wait: the reference's defects D1/D2) corrupts the output
+        # instead of silently reusing last iteration's values.
+        self.poison = os.environ.get("PCONV_POISON_HALO", "0") not in ("", "0")
 
     # -- tile I/O -----------------------------------------------------------------------------
     def _interior(self, b: np.ndarray) -> np.ndarray:
@@ -78,6 +85,8 @@ class HostTile:
         for (dy, dx), r in zip(NEIGHBOR_OFFSETS, self.nbrs):
             if r < 0 or (dy == 0 and dx == 0):
                 continue
+            if self.poison:
+                self._strip(b, dy, dx, halo=True)[:] = 0xA5
             send = torch.from_numpy(np.ascontiguousarray(self._strip(b, dy, dx, halo=False)))
             view = self._strip(b, dy, dx, halo=True)
             recv = torch.empty(view.shape, dtype=torch.uint8)

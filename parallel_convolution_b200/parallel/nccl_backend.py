@@ -17,6 +17,8 @@ comparison isolates the cost of staging + NCCL + the extra launches.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from ..models.filters import Filter
@@ -57,6 +59,9 @@ class NcclRuntime:
         self._plans: dict[int, StreamPlan] = {}
         self._ghost_key = None
         self.exchanges = 0
+        # PCONV_POISON_HALO=1: refill the ghost strips with 0xA5 before every exchange, so a region the
+        # kernel reads but the exchange did not deliver shows up as wrong pixels
+        self.poison = os.environ.get("PCONV_POISON_HALO", "0") not in ("", "0")
 
     # -- lifecycle / data (same surface as FusedRuntime) --------------------------------------------
     def close(self) -> None:
@@ -148,6 +153,9 @@ class NcclRuntime:
         dist, launched = self.dist, 0
         tile_ptr = self.mems[self.me].bufs[src_parity]
         ops = []
+        if self.poison:
+            for L in self.links:
+                L["ghost"].fill_(0xA5)
         for L in self.links:
             r0, c0, nr, ncb = L["strip"]
             K.pack_rect(tile_ptr, self.pitch, r0, c0, nr, ncb, L["send"].data_ptr(), self.stream)

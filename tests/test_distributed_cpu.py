@@ -18,10 +18,10 @@ def _port() -> int:
         return s.getsockname()[1]
 
 
-def _torchrun(nproc: int, args: list[str], timeout: int = 240) -> subprocess.CompletedProcess:
+def _torchrun(nproc: int, args: list[str], timeout: int = 240, **extra_env) -> subprocess.CompletedProcess:
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_port())] + args
-    env = dict(os.environ, OMP_NUM_THREADS="1", PYTHONPATH=ROOT)
+    env = dict(os.environ, OMP_NUM_THREADS="1", PYTHONPATH=ROOT, **extra_env)
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
 
 
@@ -33,6 +33,15 @@ def _torchrun(nproc: int, args: list[str], timeout: int = 240) -> subprocess.Com
 def test_host_backend_matches_single_process(nproc, extra):
     r = _torchrun(nproc, [os.path.join(ROOT, "scripts", "dist_check.py"), "--backend", "cpu",
                           "--height", "96", "--width", "120"] + extra)
+    assert "DIST_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("depth", [1, 3])
+def test_poisoned_halos_are_always_refreshed(depth):
+    """PCONV_POISON_HALO=1 overwrites every neighbour-facing halo with 0xA5 before each exchange: the
+    result stays exact only if all eight strips (diagonals included) are freshly received each time."""
+    r = _torchrun(4, [os.path.join(ROOT, "scripts", "dist_check.py"), "--backend", "cpu", "--height", "66",
+                      "--width", "70", "--loops", "7", "--halo-depth", str(depth)], PCONV_POISON_HALO="1")
     assert "DIST_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
