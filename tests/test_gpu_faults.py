@@ -1,7 +1,6 @@
 """Failure detection: a rank that never signals must trip the in-kernel watchdog of its neighbours
 (status flag + exception), not hang the GPU. The reference's only failure handling is MPI_Abort /
 exit() on bad arguments."""
-import numpy as np
 import pytest
 
 from conftest import random_image
