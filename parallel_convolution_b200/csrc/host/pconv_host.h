@@ -40,7 +40,7 @@ typedef struct pconv_plan_request {
     int32_t peers;                  // 1: neighbours sit on other GPUs (dearer exchanges)
     int32_t pad_;
 } pconv_plan_request_t;
-typedef struct pconv_plan {
+typedef struct pconv_plan_result {
     int32_t k, R, TH, TWB, HB, ntx, nty, waves;
     double est_us;                  // modelled time per launch (stream) / per run (resident)
 } pconv_plan_t;

@@ -39,8 +39,8 @@ extern "C" int pconv_plan(const pconv_plan_request_t* q, pconv_plan_t* out) {
     int max_band = 0;
     for (int i = 0; i < q->nbands; ++i) max_band = std::max(max_band, q->bands[i]);
     int kmax = std::min({loops, (kWarps * max_band - 1) / 2, (kRegionBytes / 2 - 64) / q->C});
-    if (q->min_nbr_rows > 0) kmax = std::min<int64_t>(kmax, q->min_nbr_rows);
-    if (q->min_nbr_cols > 0) kmax = std::min<int64_t>(kmax, q->min_nbr_cols);
+    if (q->min_nbr_rows > 0) kmax = (int)std::min<int64_t>(kmax, q->min_nbr_rows);
+    if (q->min_nbr_cols > 0) kmax = (int)std::min<int64_t>(kmax, q->min_nbr_cols);
     kmax = std::max(kmax, 1);
     const int k_lo = q->force_k > 0 ? q->force_k : 1, k_hi = q->force_k > 0 ? q->force_k : kmax;
     const double t_x = q->peers ? kExchangeUsPeer : kExchangeUs;
