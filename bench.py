@@ -176,6 +176,11 @@ def run_ours(a) -> dict | None:
     if rank != 0:
         return None
     g = eng.grid
+    from parallel_convolution_b200.utils import roofline
+    kk = int(getattr(plan, "k", 1) or 1) if plan else 1
+    roof = roofline.terms(WIDTH, HEIGHT, CHANNELS, LOOPS, a.gpus, kk, eng.filter.kind_name,
+                          g.halo_bytes_per_iteration(0, kk))
+    roof_frac = roofline.fraction(ms / K_steps * 1e-3, roof)
     return {
         "metric": METRIC, "value": round(value, 1), "unit": "Mpx/s", "n_gpus": a.gpus,
         "steps": K_steps, "warmup": W, "ms_per_step": round(ms / K_steps, 5),
@@ -192,6 +197,7 @@ def run_ours(a) -> dict | None:
                    "cache": f"inputs rotate through a device pool of {pool} images/GPU "
                             f"({pool * tile_bytes >> 20} MiB > L2 {l2 >> 20} MiB); no L2 flush needed",
                    "timed_region": "pool->tile device copy + halo protocol + all iterations of every step",
+                   "roofline_s_per_step": roof, "fraction_of_binding_roofline": round(roof_frac, 4),
                    "baseline_mpx_s": BASELINE_MPX_S,
                    "baseline_source": "BASELINE.md: MPI+OMP rgb 1920x2520, 16 processes (best published RGB rate)"},
         "clocks": clocks,
