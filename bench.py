@@ -167,7 +167,7 @@ def run_ours(a) -> dict | None:
     rep = eng.report
     impl = eng._impl
     kmode = impl.choose_mode(LOOPS) if hasattr(impl, "choose_mode") else "stream"
-    plan = impl.resident_plan(LOOPS) if kmode == "resident" else impl.plan(LOOPS)
+    plan = impl.plan_for(kmode, LOOPS) if hasattr(impl, "plan_for") else impl.plan(LOOPS)
     h2d = allsum(tile_bytes)
     eng.close()
     if dist:

@@ -16,6 +16,18 @@
 // Two buffer parities make the strips double-buffered: writing version b never races with a
 // neighbour still reading version b-1, and passing step 3 of exchange b proves every neighbour is
 // done with version b-1. The final interior goes to the parity that holds no live strips.
+// Split-phase variant (resident2_kernel.cuh, params.dual = 1): the exchange above is *exposed* — every
+// tile needs its neighbours' block-b state exactly when it finishes block b itself. The split-phase
+// kernel gives each CTA two vertically stacked virtual tiles and alternates between them; CTA rows
+// alternate the order (even rows top-first, odd rows bottom-first), so virtual tile rows are phased
+// F S S F F S S F ... While one tile computes, the other tile's registers are dead, so its halo is
+// re-loaded mid-compute straight into them and lands in the background; every inter-CTA dependency
+// then has at least a quarter period of slack. What stays zero-slack is the part of an F tile's halo
+// that faces its sibling row (sibling: same CTA, program order; the two lateral corner pieces: flags).
+// Deadlock-free by induction: F publishes of epoch b depend on epoch b-1 only, S publishes of epoch b
+// on F publishes of epoch b. The WAR argument of the parity double buffer is unchanged (a tile's flag
+// for epoch b+1 is set after both parts of its reload for block b were consumed).
+//
 // This is the north-star design of BASELINE.json: persistent, double-buffered, P2P loads of
 // neighbour borders inside the stencil kernel, no NCCL/MPI on the path. It replaces the reference's
 // per-iteration MPI_Isend/Irecv/Wait schedule (mpi/mpi_conv.c:164-248) and its launch-per-
@@ -24,15 +36,16 @@
 
 #include <cstring>
 
+#include "resident2_kernel.cuh"
 #include "resident_kernel.cuh"
 
 namespace pconv {
 
-static ResidentFn pick_kernel(int kind, int C, int R) {
+static ResidentFn pick_kernel(int kind, int C, int R, bool dual = false) {
     switch (kind) {
-        case PCONV_KIND_SEP121: return pick_resident_sep(C, R);
-        case PCONV_KIND_INT: return pick_resident_int(C, R);
-        case PCONV_KIND_F32: return pick_resident_f32(C, R);
+        case PCONV_KIND_SEP121: return dual ? pick_resident2_sep(C, R) : pick_resident_sep(C, R);
+        case PCONV_KIND_INT: return dual ? pick_resident2_int(C, R) : pick_resident_int(C, R);
+        case PCONV_KIND_F32: return dual ? pick_resident2_f32(C, R) : pick_resident_f32(C, R);
         default: return nullptr;
     }
 }
@@ -51,14 +64,17 @@ extern "C" int pconv_resident_launch(const pconv_resident_params_t* p, void* str
     const int64_t tile_rows = g.row_lo[2] - g.row_lo[1], tile_cb = g.cb_lo[2] - g.cb_lo[1];
     if ((int64_t)p->nty * p->TH < tile_rows || (int64_t)p->ntx * p->TWB < tile_cb)
         return pconv_rt::fail("CTA grid does not cover the tile");
-    const int grid = p->nty * p->ntx;
+    const bool dual = p->dual != 0;   // split-phase: nty counts virtual tile rows, two per CTA
+    if (dual && (p->nty & 1)) return pconv_rt::fail("split-phase resident kernel needs an even number of tile rows");
+    if ((int64_t)(p->nty + 2) * (p->ntx + 2) > 1024) return pconv_rt::fail("CTA flag grid exceeds its 4 KB pad");
+    const int grid = (dual ? p->nty / 2 : p->nty) * p->ntx;
     if (grid < 1 || grid > pconv_rt::sm_count()) return pconv_rt::fail("resident grid exceeds the SM count");
     for (int s = 0; s < 3; s += 2) {
         const int64_t nr = g.row_lo[s + 1] - g.row_lo[s], nc = g.cb_lo[s + 1] - g.cb_lo[s];
         if ((nr > 0 && nr < p->k) || (nc > 0 && nc < (int64_t)p->k * g.C))
             return pconv_rt::fail("halo depth exceeds a neighbouring tile");
     }
-    ResidentFn fn = pick_kernel(p->filt.kind, g.C, p->R);
+    ResidentFn fn = pick_kernel(p->filt.kind, g.C, p->R, dual);
     if (!fn) return pconv_rt::fail("unsupported (filter kind, channels, band height) combination");
 
     ResidentArgs a;
@@ -86,8 +102,18 @@ extern "C" int pconv_resident_launch(const pconv_resident_params_t* p, void* str
     return 0;
 }
 
-extern "C" int pconv_resident_prepare(int kind, int C, int R) {
-    ResidentFn fn = pick_kernel(kind, C, R);
+extern "C" int pconv_resident2_band_heights(int kind, int* out, int cap) {
+    int n = 0;
+#define PUSH(RR) if (n < cap) out[n] = RR; ++n;
+    if (kind == PCONV_KIND_F32) { PCONV_RES2_R_F32(PUSH) }
+    else if (kind == PCONV_KIND_INT) { PCONV_RES2_R_INT(PUSH) }
+    else { PCONV_RES2_R_SEP(PUSH) }
+#undef PUSH
+    return n;
+}
+
+extern "C" int pconv_resident_prepare(int kind, int C, int R, int dual) {
+    ResidentFn fn = pick_kernel(kind, C, R, dual != 0);
     if (!fn) return pconv_rt::fail("unsupported (filter kind, channels, band height) combination");
     cudaFuncAttributes at;
     cudaError_t e = cudaFuncGetAttributes(&at, (const void*)fn);

@@ -25,6 +25,9 @@ double bytes_per_clk(int kind) {
 }
 constexpr double kClockGHz = 1.8, kLaunchUs = 4.0, kLoadBytesPerUsPerSm = 40e3;
 constexpr double kExchangeUs = 3.0, kExchangeUsPeer = 6.0;
+// split-phase resident kernel: what is left exposed of an exchange (issue time of the strip stores
+// and halo loads, the sibling hand-over)
+constexpr double kExchangeUsDual = 1.0, kExchangeUsDualPeer = 2.0;
 
 int roundup(int v, int m) { return (v + m - 1) / m * m; }
 int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -43,7 +46,9 @@ extern "C" int pconv_plan(const pconv_plan_request_t* q, pconv_plan_t* out) {
     if (q->min_nbr_cols > 0) kmax = (int)std::min<int64_t>(kmax, q->min_nbr_cols);
     kmax = std::max(kmax, 1);
     const int k_lo = q->force_k > 0 ? q->force_k : 1, k_hi = q->force_k > 0 ? q->force_k : kmax;
-    const double t_x = q->peers ? kExchangeUsPeer : kExchangeUs;
+    const bool dual = q->resident && q->dual;
+    const double t_x = dual ? (q->peers ? kExchangeUsDualPeer : kExchangeUsDual)
+                            : (q->peers ? kExchangeUsPeer : kExchangeUs);
     bool found = false;
     double best = 0.0;
     for (int k = k_lo; k <= k_hi; ++k) {
@@ -55,16 +60,19 @@ extern "C" int pconv_plan(const pconv_plan_request_t* q, pconv_plan_t* out) {
             if (q->force_R > 0 && R != q->force_R) continue;
             const int RH = kWarps * R, th_max = RH - 2 * k;
             if (th_max < (q->resident ? k : 1)) continue;
-            const int64_t nty = ceil_div(q->tile_rows, th_max);
-            if (q->resident && ntx * nty > sms) continue;   // every CTA must be co-resident
+            int64_t nty = ceil_div(q->tile_rows, th_max);
+            if (dual) nty += nty & 1;                       // two virtual tile rows per CTA
+            if (q->resident && ntx * nty > (dual ? 2 : 1) * (int64_t)sms) continue;   // every CTA co-resident
+            if (dual && (nty + 2) * (ntx + 2) > 1024) continue;   // CTA flag pad
             int TH = (int)ceil_div(q->tile_rows, nty);      // balance rows over the same tile count
             if (q->resident) TH = std::max(TH, k);
-            const int64_t waves = ceil_div(ntx * nty, sms);
+            const int64_t waves = ceil_div(dual ? ntx * nty / 2 : ntx * nty, sms);
             double total, per_launch;
             if (q->resident) {
                 const int64_t nblocks = ceil_div(loops, k);
-                total = kLaunchUs + (RH * (double)kRegionBytes + (double)TH * TWB) / kLoadBytesPerUsPerSm +
-                        nblocks * (k * RH * (double)kRegionBytes / rate) + (nblocks - 1) * t_x;
+                const double regions = dual ? 2.0 : 1.0;     // per CTA, computed back to back
+                total = kLaunchUs + regions * (RH * (double)kRegionBytes + (double)TH * TWB) / kLoadBytesPerUsPerSm +
+                        nblocks * regions * (k * RH * (double)kRegionBytes / rate) + (nblocks - 1) * regions * t_x;
                 per_launch = total;
             } else {
                 const double t_tile = RH * (double)kRegionBytes / kLoadBytesPerUsPerSm +

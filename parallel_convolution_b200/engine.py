@@ -40,7 +40,7 @@ class EngineConfig:
     workers: int | None = None       # single-process: number of virtual ranks (default 1)
     grid: tuple[int, int] | None = None
     halo_depth: int | None = None    # temporal-blocking depth k (None: planner decides)
-    mode: str = "auto"               # fused backend: auto | stream | resident
+    mode: str = "auto"               # fused backend: auto | stream | resident | resident2
     threads: int = 0                 # cpu backend: OpenMP threads per rank
     device: int | None = None        # CUDA device index (default: LOCAL_RANK or 0)
     timeout_ms: float = 10_000.0     # in-kernel watchdog for neighbour flags

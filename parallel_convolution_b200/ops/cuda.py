@@ -44,7 +44,7 @@ class ResidentParams(C.Structure):
                 ("loops", C.c_int32), ("k", C.c_int32), ("TH", C.c_int32), ("TWB", C.c_int32),
                 ("HB", C.c_int32), ("R", C.c_int32), ("nty", C.c_int32), ("ntx", C.c_int32),
                 ("cta_flags", C.c_void_p), ("remote_cta_flags", C.c_void_p * 9),
-                ("epoch_base", C.c_uint32), ("pad_", C.c_uint32), ("sync", Sync)]
+                ("epoch_base", C.c_uint32), ("dual", C.c_uint32), ("sync", Sync)]
 
 
 class CudaError(RuntimeError):
@@ -134,6 +134,16 @@ def band_heights(kind: int) -> list[int]:
     """Band heights R (rows per warp; region = 16*R rows) compiled for a filter kind."""
     buf = (C.c_int * 16)()
     n = int(lib().pconv_stream_band_heights(kind, buf, 16))
+    return [int(buf[i]) for i in range(n)]
+
+
+def resident2_band_heights(kind: int) -> list[int]:
+    """Band heights (rows per warp per virtual tile) compiled for the split-phase resident kernel."""
+    L = lib()
+    if not hasattr(L, "pconv_resident2_band_heights"):
+        return []
+    buf = (C.c_int * 16)()
+    n = int(L.pconv_resident2_band_heights(kind, buf, 16))
     return [int(buf[i]) for i in range(n)]
 
 
@@ -265,8 +275,9 @@ def unpack_rect(tile: int, pitch: int, row0: int, byte0: int, rows: int, nbytes:
            "unpack_rect")
 
 
-def kernel_prepare(kind: int, channels: int, band: int, resident: bool = False) -> None:
-    _check(lib().pconv_kernel_prepare(kind, channels, band, 1 if resident else 0), "kernel_prepare")
+def kernel_prepare(kind: int, channels: int, band: int, resident: bool | int = False) -> None:
+    """``resident``: False/0 stream kernel, True/1 resident kernel, 2 split-phase resident kernel."""
+    _check(lib().pconv_kernel_prepare(kind, channels, band, int(resident)), "kernel_prepare")
 
 
 def stream_launch(p: StreamParams, stream: int) -> None:

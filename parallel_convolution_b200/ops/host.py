@@ -36,7 +36,7 @@ class PlanRequest(C.Structure):
                 ("min_nbr_cols", C.c_int64), ("C", C.c_int32), ("kind", C.c_int32),
                 ("loops", C.c_int32), ("sms", C.c_int32), ("bands", C.c_int32 * 8),
                 ("nbands", C.c_int32), ("force_k", C.c_int32), ("force_R", C.c_int32),
-                ("resident", C.c_int32), ("peers", C.c_int32), ("pad_", C.c_int32)]
+                ("resident", C.c_int32), ("peers", C.c_int32), ("dual", C.c_int32)]
 
 
 class PlanResult(C.Structure):
@@ -114,7 +114,8 @@ def split(extent: int, parts: int, idx: int) -> tuple[int, int]:
 
 def plan(tile_rows: int, tile_cb: int, Cn: int, kind: int, loops: int, bands: list[int], *,
          min_nbr_rows: int = 0, min_nbr_cols: int = 0, sms: int = 148, force_k: int = 0,
-         force_R: int = 0, resident: bool = False, peers: bool = False) -> PlanResult | None:
+         force_R: int = 0, resident: bool = False, peers: bool = False,
+         dual: bool = False) -> PlanResult | None:
     """Native launch planner (csrc/host/planner.cpp). None when no plan is feasible."""
     q = PlanRequest()
     q.tile_rows, q.tile_cb, q.min_nbr_rows, q.min_nbr_cols = tile_rows, tile_cb, min_nbr_rows, min_nbr_cols
@@ -123,7 +124,7 @@ def plan(tile_rows: int, tile_cb: int, Cn: int, kind: int, loops: int, bands: li
         q.bands[i] = b
     q.nbands = min(len(bands), 8)
     q.force_k, q.force_R = force_k or 0, force_R or 0
-    q.resident, q.peers = int(resident), int(peers)
+    q.resident, q.peers, q.dual = int(resident), int(peers), int(dual)
     out = PlanResult()
     rc = lib().pconv_plan(C.byref(q), C.byref(out))
     if rc < 0:

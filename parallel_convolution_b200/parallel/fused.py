@@ -157,6 +157,7 @@ class TileDriver:
         p.filt = self.filt.spec
         p.loops, p.k, p.TH, p.TWB, p.HB, p.R = loops, plan.k, plan.TH, plan.TWB, plan.HB, plan.R
         p.nty, p.ntx = plan.nty, plan.ntx
+        p.dual = 1 if plan.dual else 0
         p.cta_flags = self.mem.cta_flags
         p.epoch_base = cta_epoch
         p.sync.local_flags = self.mem.flags + (BANK1 if wait_bank1 else 0)
@@ -218,8 +219,9 @@ class TileDriver:
 
 def make_resident_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int | None = None,
                        sms: int | None = None, bands: list[int] | None = None,
-                       band: int | None = None, peers: bool = False) -> StreamPlan | None:
-    """Plan for the persistent resident kernel, or None when the tile does not fit on chip."""
+                       band: int | None = None, peers: bool = False, dual: bool = False) -> StreamPlan | None:
+    """Plan for the persistent resident kernel (``dual``: its split-phase variant), or None when the
+    tile does not fit on chip."""
     from .plan import plan_resident
     if not grid.exact and grid.workers > 1:
         return None      # the mirrored CTA-flag rings assume identical tile shapes on every rank
@@ -233,7 +235,7 @@ def make_resident_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int
     return plan_resident(grid.max_tile_rows(), grid.max_tile_cols() * Cn, Cn, filt.kind, max(loops, 1),
                          min_nbr_rows=grid.min_tile_rows() if multi_r else None,
                          min_nbr_cols=grid.min_tile_cols() if multi_c else None,
-                         force_k=halo_depth, force_R=band, peers=peers, **kw)
+                         force_k=halo_depth, force_R=band, peers=peers, dual=dual, **kw)
 
 
 def make_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int | None = None,

@@ -13,6 +13,8 @@ synchronises twice per run (before: inputs in place; after: results readable), n
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from ..models.filters import Filter
@@ -21,6 +23,10 @@ from .decomposition import TileGrid
 from .fused import (RankMemory, TileDriver, make_plan, make_resident_plan,
                     tile_pitch)
 from .plan import StreamPlan
+
+# Whether "auto" lets the autotuner try the split-phase resident kernel (explicit --mode resident2
+# always works). Single-GPU runs only until it has been validated across NVLink.
+AUTO_RESIDENT2 = os.environ.get("PCONV_RESIDENT2", "0") == "1"
 
 
 class FusedRuntime:
@@ -36,6 +42,7 @@ class FusedRuntime:
         self.stream = K.stream_create()
         self.sms = K.sm_count()
         self.bands = K.band_heights(filt.kind)
+        self.bands2 = K.resident2_band_heights(filt.kind)    # split-phase resident kernel
         rows = grid.max_tile_rows()
         self.peers = None
         if world > 1:
@@ -60,6 +67,7 @@ class FusedRuntime:
         self.multi = grid.workers > 1
         self._plans: dict[int, StreamPlan] = {}
         self._rplans: dict[int, StreamPlan | None] = {}
+        self._r2plans: dict[int, StreamPlan | None] = {}
         # virtual ranks in resident mode need their persistent kernels co-resident: one stream each
         self._rank_streams = ({r: K.stream_create() for r in self.local_ranks}
                               if len(self.local_ranks) > 1 else {})
@@ -132,13 +140,25 @@ class FusedRuntime:
         self._first_wait = self.epoch
         return len(self.drivers)
 
-    def resident_plan(self, loops: int) -> StreamPlan | None:
-        if loops not in self._rplans:
+    def resident_plan(self, loops: int, dual: bool = False) -> StreamPlan | None:
+        """Plan of the persistent kernel (``dual``: its split-phase variant); None if it cannot hold the tile."""
+        cache = self._r2plans if dual else self._rplans
+        if loops not in cache:
             nloc = len(self.local_ranks)
-            self._rplans[loops] = make_resident_plan(
-                self.grid, self.filt, loops, self.halo_depth, self.sms // nloc, self.bands, self.band,
-                peers=self.world > 1)
-        return self._rplans[loops]
+            bands = self.bands2 if dual else self.bands
+            if dual and (not bands or (self.band and self.band not in bands)):
+                cache[loops] = None
+            else:
+                cache[loops] = make_resident_plan(
+                    self.grid, self.filt, loops, self.halo_depth, self.sms // nloc, bands, self.band,
+                    peers=self.world > 1, dual=dual)
+        return cache[loops]
+
+    def _plan_cache(self, mode: str) -> dict:
+        return {"stream": self._plans, "resident": self._rplans, "resident2": self._r2plans}[mode]
+
+    def plan_for(self, mode: str, loops: int) -> StreamPlan | None:
+        return self.plan(loops) if mode == "stream" else self.resident_plan(loops, mode == "resident2")
 
     # -- on-device autotuning ----------------------------------------------------------------------
     def autotune(self, loops: int, max_candidates: int = 14, reps: int = 2) -> dict:
@@ -150,7 +170,6 @@ class FusedRuntime:
         before loading real input."""
         if loops <= 0:
             return {}
-        base_s, base_r = self.plan(loops), (self.resident_plan(loops) if self.mode != "stream" else None)
         cands: list[tuple[str, StreamPlan]] = []
 
         def add(mode: str, k: int, R: int) -> None:
@@ -158,35 +177,44 @@ class FusedRuntime:
                 if mode == "stream":
                     p = make_plan(self.grid, self.filt, loops, k, self.sms, self.bands, R)
                 else:
+                    dual = mode == "resident2"
                     p = make_resident_plan(self.grid, self.filt, loops, k, self.sms // len(self.local_ranks),
-                                           self.bands, R, peers=self.world > 1)
+                                           self.bands2 if dual else self.bands, R, peers=self.world > 1,
+                                           dual=dual)
             except ValueError:
                 return
             if p is not None and (mode, p) not in cands:
                 cands.append((mode, p))
 
         modes = [m for m in ("stream", "resident") if self.mode in ("auto", m)]
+        if self.bands2 and (self.mode == "resident2" or (self.mode == "auto" and AUTO_RESIDENT2)):
+            modes.append("resident2")
+        per_mode = max(4, max_candidates // max(1, len(modes)))
         for mode in modes:
-            base = base_s if mode == "stream" else base_r
+            base = self.plan_for(mode, loops)
             if base is None:
                 continue
+            mine = len(cands)
             cands.append((mode, base))
+            bands = self.bands2 if mode == "resident2" else self.bands
             for k in sorted({max(1, base.k - 2), max(1, base.k - 1), base.k + 1, base.k + 2, base.k + 5,
                              max(1, base.k // 2), base.k * 2} - {base.k}):
                 if self.halo_depth or k > loops:
                     continue
-                for R in ([base.R] + [b for b in self.bands if b != base.R]):
+                for R in ([base.R] + [b for b in bands if b != base.R]):
                     if self.band and R != self.band:
                         continue
                     add(mode, k, R)
-        # rank by the model, measure the most promising ones
-        cands.sort(key=lambda mp: mp[1].est_us_per_launch * (1 if mp[0] == "resident" else -(-loops // mp[1].k)))
-        cands = cands[:max_candidates]
-        saved = (self.mode, dict(self._plans), dict(self._rplans))
+            # rank this mode's candidates by the model and keep its most promising ones (the models of
+            # different kernels are not comparable with each other — the measurement decides that)
+            own = sorted(cands[mine:], key=lambda mp: mp[1].est_us_per_launch *
+                         (-(-loops // mp[1].k) if mp[0] == "stream" else 1))
+            cands[mine:] = own[:per_mode]
+        saved = (self.mode, dict(self._plans), dict(self._rplans), dict(self._r2plans))
         results = []
         for mode, p in cands:
             self.mode = mode
-            (self._plans if mode == "stream" else self._rplans)[loops] = p
+            self._plan_cache(mode)[loops] = p
             best = None
             try:
                 self.prepare(loops)
@@ -217,14 +245,14 @@ class FusedRuntime:
                 best = float(t.item())
             if best is not None:
                 results.append((best, mode, p))
-        self.mode, self._plans, self._rplans = saved
+        self.mode, self._plans, self._rplans, self._r2plans = saved
         if not results:
             return {}
         results.sort(key=lambda r: r[0])
         ms, mode, p = results[0]
         self._tuned = getattr(self, "_tuned", {})
         self._tuned[loops] = mode
-        (self._plans if mode == "stream" else self._rplans)[loops] = p
+        self._plan_cache(mode)[loops] = p
         return {"mode": mode, "plan": dict(p.__dict__), "ms": ms,
                 "tried": [(round(r[0], 4), r[1], r[2].k, r[2].R) for r in results]}
 
@@ -232,9 +260,9 @@ class FusedRuntime:
         tuned = getattr(self, "_tuned", {}).get(loops)
         if tuned and self.mode == "auto":
             return tuned
-        if self.mode in ("stream", "resident"):
-            if self.mode == "resident" and self.resident_plan(loops) is None:
-                raise ValueError("resident mode requested but the tile does not fit on chip")
+        if self.mode in ("stream", "resident", "resident2"):
+            if self.mode != "stream" and self.plan_for(self.mode, loops) is None:
+                raise ValueError(f"{self.mode} mode requested but the tile does not fit on chip")
             return self.mode
         # "auto", from measurements on B200 (profiles/README.md): on 1-2 GPUs one in-kernel exchange
         # costs about as much as a relaunch + reload, and streaming wins by 4-8 % (0.47 vs 0.51 ms on
@@ -244,8 +272,8 @@ class FusedRuntime:
             return "resident"
         return "stream"
 
-    def _enqueue_resident(self, loops: int) -> tuple[StreamPlan, int]:
-        plan = self.resident_plan(loops)
+    def _enqueue_resident(self, loops: int, dual: bool = False) -> tuple[StreamPlan, int]:
+        plan = self.resident_plan(loops, dual)
         nblocks = -(-loops // plan.k)
         first_wait, self._first_wait = getattr(self, "_first_wait", 0), 0
         signal = self.epoch + 1 if self.multi else 0
@@ -275,8 +303,9 @@ class FusedRuntime:
         """Enqueue ``loops`` iterations on the runtime stream; returns (plan, kernel launches)."""
         if loops <= 0:
             return None, 0
-        if self.choose_mode(loops) == "resident":
-            return self._enqueue_resident(loops)
+        mode = self.choose_mode(loops)
+        if mode != "stream":
+            return self._enqueue_resident(loops, mode == "resident2")
         plan = self.plan(loops)
         ks = plan.launches(loops)
         n = len(self.local_ranks)
@@ -357,8 +386,9 @@ class FusedRuntime:
         """Plan and force the module load of the kernel that ``loops`` will use (one-time cost)."""
         if loops <= 0:
             return
-        resident = self.choose_mode(loops) == "resident"
-        plan = self.resident_plan(loops) if resident else self.plan(loops)
+        mode = self.choose_mode(loops)
+        plan = self.plan_for(mode, loops)
+        resident = {"stream": 0, "resident": 1, "resident2": 2}[mode]
         key = (plan.R, resident)
         if key not in getattr(self, "_prepared", set()):
             K.kernel_prepare(self.filt.kind, self.grid.channels, plan.R, resident)

@@ -19,6 +19,8 @@ DEFAULT_SMS = 148
 # Band heights compiled into libpconv_cuda.so (csrc/cuda/stream_kernel.cu); refined from the
 # library at runtime (ops.cuda.band_heights).
 DEFAULT_BANDS = {KIND_SEP121: [2, 4, 7, 10, 14], KIND_INT: [2, 4, 7, 10], KIND_F32: [2, 4, 6, 8, 10]}
+# split-phase resident kernel (csrc/cuda/resident2_kernel.cuh): rows per warp per virtual tile
+DEFAULT_DUAL_BANDS = {KIND_SEP121: [2, 4, 5, 7], KIND_INT: [2, 4, 5], KIND_F32: [2, 4, 5]}
 
 
 @dataclass(frozen=True)
@@ -32,6 +34,7 @@ class StreamPlan:
     nty: int
     waves: int
     est_us_per_launch: float
+    dual: bool = False   # split-phase resident kernel: nty counts virtual tile rows, two per CTA
 
     @property
     def RH(self) -> int:
@@ -43,10 +46,10 @@ class StreamPlan:
         return [self.k] * full + ([rem] if rem else [])
 
 
-def _to_plan(r) -> StreamPlan | None:
+def _to_plan(r, dual: bool = False) -> StreamPlan | None:
     if r is None:
         return None
-    return StreamPlan(r.k, r.R, r.TH, r.TWB, r.HB, r.ntx, r.nty, r.waves, float(r.est_us))
+    return StreamPlan(r.k, r.R, r.TH, r.TWB, r.HB, r.ntx, r.nty, r.waves, float(r.est_us), dual)
 
 
 def plan_stream(tile_rows: int, tile_cb: int, C: int, kind: int, loops: int, *,
@@ -64,7 +67,11 @@ def plan_stream(tile_rows: int, tile_cb: int, C: int, kind: int, loops: int, *,
 def plan_resident(tile_rows: int, tile_cb: int, C: int, kind: int, loops: int, *,
                   min_nbr_rows: int | None = None, min_nbr_cols: int | None = None,
                   sms: int = DEFAULT_SMS, bands: list[int] | None = None, peers: bool = False,
-                  force_k: int | None = None, force_R: int | None = None) -> StreamPlan | None:
-    return _to_plan(H.plan(tile_rows, tile_cb, C, kind, loops, sorted(bands or DEFAULT_BANDS[kind]),
+                  force_k: int | None = None, force_R: int | None = None,
+                  dual: bool = False) -> StreamPlan | None:
+    """``dual``: plan the split-phase kernel (``bands`` are then its per-virtual-tile heights)."""
+    default = DEFAULT_DUAL_BANDS if dual else DEFAULT_BANDS
+    return _to_plan(H.plan(tile_rows, tile_cb, C, kind, loops, sorted(bands or default[kind]),
                            min_nbr_rows=min_nbr_rows or 0, min_nbr_cols=min_nbr_cols or 0, sms=sms,
-                           force_k=force_k or 0, force_R=force_R or 0, resident=True, peers=peers))
+                           force_k=force_k or 0, force_R=force_R or 0, resident=True, peers=peers,
+                           dual=dual), dual)

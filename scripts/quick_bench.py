@@ -29,7 +29,7 @@ def main():
     g = TileGrid.create(a.height, a.width, a.channels, a.workers)
     vc = VirtualCluster(g, f, halo_depth=a.k or None, band=a.band or None, mode=a.mode)
     vc.synth(1)
-    plan = vc.rt.resident_plan(a.loops) if vc.rt.choose_mode(a.loops) == 'resident' else vc.rt.plan(a.loops)
+    plan = vc.rt.plan_for(vc.rt.choose_mode(a.loops), a.loops)
     vc.run(a.loops)
     K.device_sync()
     best = 1e9
