@@ -11,7 +11,13 @@ Public API::
     eng = ConvEngine(width=1920, height=2520, channels=3, filter="gaussian")
     out = eng.run(image_uint8, loops=100)
 """
-from .models.filters import Filter, available as available_filters  # noqa: F401
+import os as _os
+
+# Must be in the environment before ANY library creates the CUDA context (see ops/cuda.py): persistent
+# kernels of several virtual ranks need one hardware queue each.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+from .models.filters import Filter, available as available_filters  # noqa: E402,F401
 
 __version__ = "0.1.0"
 

@@ -131,6 +131,13 @@ resident2_kernel(const __grid_constant__ ResidentArgs A) {
                     ? wait_flag<false>(fl, epoch, A.sync.timeout_ns, A.sync.status)   // local CTA
                     : wait_flag<true>(fl, epoch, A.sync.timeout_ns, A.sync.status);   // other GPU
                 atomicMax(&s_wait_ns, (unsigned long long)ns);
+                if (ns > A.sync.timeout_ns && A.sync.status != nullptr) {
+                    // post-mortem of the first wait that timed out: who waited for whom, and what was there
+                    unsigned long long* st = reinterpret_cast<unsigned long long*>(A.sync.status);
+                    const unsigned long long what = 1ull << 63 | (unsigned long long)vi << 48 |
+                        (unsigned long long)tj << 40 | (unsigned long long)d << 32 | (unsigned long long)epoch;
+                    if (atomicCAS(st + 9, 0ull, what) == 0ull) st[10] = (unsigned long long)ld_acquire_sys(fl);
+                }
             }
         }
         __syncthreads();

@@ -74,6 +74,11 @@ extern "C" int pconv_resident_launch(const pconv_resident_params_t* p, void* str
         if ((nr > 0 && nr < p->k) || (nc > 0 && nc < (int64_t)p->k * g.C))
             return pconv_rt::fail("halo depth exceeds a neighbouring tile");
     }
+    // per-CTA flags only cover the eight surrounding CTAs (see planner.cpp)
+    if (g.row_lo[3] > g.row_lo[2] && tile_rows - (int64_t)(p->nty - 1) * p->TH < p->k)
+        return pconv_rt::fail("last CTA row is shallower than the halo and a rank lies below");
+    if (g.cb_lo[3] > g.cb_lo[2] && tile_cb - (int64_t)(p->ntx - 1) * p->TWB < (int64_t)p->k * g.C)
+        return pconv_rt::fail("last CTA column is narrower than the halo and a rank lies to the right");
     ResidentFn fn = pick_kernel(p->filt.kind, g.C, p->R, dual);
     if (!fn) return pconv_rt::fail("unsupported (filter kind, channels, band height) combination");
 

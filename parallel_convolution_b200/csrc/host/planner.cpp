@@ -66,6 +66,15 @@ extern "C" int pconv_plan(const pconv_plan_request_t* q, pconv_plan_t* out) {
             if (dual && (nty + 2) * (ntx + 2) > 1024) continue;   // CTA flag pad
             int TH = (int)ceil_div(q->tile_rows, nty);      // balance rows over the same tile count
             if (q->resident) TH = std::max(TH, k);
+            if (q->resident) {
+                // A CTA only awaits the flags of its eight surrounding CTAs: with a rank below / to the
+                // right, the last CTA row / column must itself be at least one halo deep, or the halo of
+                // the row / column before it would reach past it into that rank unsynchronised.
+                const int64_t last_rows = q->tile_rows - (nty - 1) * (int64_t)TH;
+                const int64_t last_cb = q->tile_cb - (ntx - 1) * (int64_t)TWB;
+                if (q->min_nbr_rows > 0 && last_rows < k) continue;
+                if (q->min_nbr_cols > 0 && last_cb < (int64_t)k * q->C) continue;
+            }
             const int64_t waves = ceil_div(dual ? ntx * nty / 2 : ntx * nty, sms);
             double total, per_launch;
             if (q->resident) {

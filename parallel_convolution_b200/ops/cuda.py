@@ -15,6 +15,13 @@ from .host import FilterSpec
 
 DIRS = 9
 SELF = 4
+# Persistent kernels of several virtual ranks must run CONCURRENTLY (they spin on each other's flags).
+# Streams are multiplexed onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); two rank
+# streams sharing a queue serialise their kernels behind each other's event records — a deadlock that
+# only the watchdog ends. The variable is read when the CUDA context is created, so set it before the
+# library makes its first CUDA call (no effect if another library already initialised CUDA).
+MAX_CONNECTIONS = 32
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", str(MAX_CONNECTIONS))
 
 
 class Geometry(C.Structure):

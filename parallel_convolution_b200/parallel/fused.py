@@ -27,7 +27,8 @@ from .plan import StreamPlan, plan_stream
 
 FLAG_BYTES = 256      # bank 0 (+0): launch epochs, bank 1 (+64): "input ready" step counters
 BANK1 = 64
-STATUS_WORDS = 9      # u64: error, max wait ns, sum wait ns, waits, probe: publish/wait/reload/compute ns, exchanges
+STATUS_WORDS = 11     # u64: error, max wait ns, sum wait ns, waits, probe: publish/wait/reload/compute ns, exchanges,
+                      # first timed-out wait of the split-phase kernel (packed vi/tj/dir/epoch), flag value seen
 CTA_FLAG_BYTES = 4096  # resident kernel: (nty+2)*(ntx+2) u32 epochs, nty*ntx <= #SMs
 # control block layout (one cudaMalloc, one IPC handle): flags | counter | status | cta_flags
 OFF_COUNTER, OFF_STATUS, OFF_CTA = FLAG_BYTES, FLAG_BYTES + 64, FLAG_BYTES + 64 + 128
@@ -214,6 +215,10 @@ class TileDriver:
         self.probe = {"publish_us": float(out[4]) / 1e3, "wait_us": float(out[5]) / 1e3,
                       "reload_us": float(out[6]) / 1e3, "compute_us": float(out[7]) / 1e3,
                       "exchanges": int(out[8])}
+        if out[9]:
+            w = int(out[9])
+            self.probe["timed_out_wait"] = {"vi": (w >> 48) & 0x7fff, "tj": (w >> 40) & 0xff, "dir": (w >> 32) & 0xff,
+                                            "epoch": w & 0xffffffff, "flag_seen": int(out[10])}
         return bool(out[0]), float(out[1]) / 1e3, float(out[2]) / 1e3, int(out[3])
 
 

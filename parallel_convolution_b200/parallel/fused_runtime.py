@@ -68,9 +68,10 @@ class FusedRuntime:
         self._plans: dict[int, StreamPlan] = {}
         self._rplans: dict[int, StreamPlan | None] = {}
         self._r2plans: dict[int, StreamPlan | None] = {}
-        # virtual ranks in resident mode need their persistent kernels co-resident: one stream each
+        # virtual ranks in resident mode need their persistent kernels co-resident: one stream each,
+        # and no two of them on one hardware queue (ops.cuda.MAX_CONNECTIONS) — beyond that, stream mode
         self._rank_streams = ({r: K.stream_create() for r in self.local_ranks}
-                              if len(self.local_ranks) > 1 else {})
+                              if 1 < len(self.local_ranks) < K.MAX_CONNECTIONS - 2 else {})
 
     # -- lifecycle ------------------------------------------------------------------------------
     def close(self) -> None:
@@ -143,6 +144,8 @@ class FusedRuntime:
     def resident_plan(self, loops: int, dual: bool = False) -> StreamPlan | None:
         """Plan of the persistent kernel (``dual``: its split-phase variant); None if it cannot hold the tile."""
         cache = self._r2plans if dual else self._rplans
+        if len(self.local_ranks) > 1 and not self._rank_streams:
+            return None        # too many virtual ranks for concurrent persistent kernels
         if loops not in cache:
             nloc = len(self.local_ranks)
             bands = self.bands2 if dual else self.bands

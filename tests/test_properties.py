@@ -73,3 +73,20 @@ def test_integer_filters_are_exact_in_fp32(w, s, seed):
     want = np.clip(S >> s, 0, 255).astype(np.uint8)
     assert np.array_equal(host.oracle(img, f.spec, 1), want)
     assert np.array_equal(host.cpu_run_image(img, f.spec, 1), want)
+
+
+@settings(max_examples=150, deadline=None)
+@given(rows=st.integers(40, 4000), cb=st.integers(64, 12000), c=st.sampled_from([1, 3, 4]),
+       kind=st.sampled_from([0, 1, 2]), loops=st.integers(1, 120), sms=st.sampled_from([37, 74, 148]))
+def test_split_phase_plans_are_launchable(rows, cb, c, kind, loops, sms):
+    """Plans for the split-phase resident kernel: two virtual tile rows per CTA, everything co-resident."""
+    from parallel_convolution_b200.parallel.plan import plan_resident
+    cb = cb // c * c or c
+    p = plan_resident(rows, cb, c, kind, loops, sms=sms, dual=True)
+    if p is None:
+        return
+    assert p.dual and p.nty % 2 == 0 and (p.nty // 2) * p.ntx <= sms
+    assert (p.nty + 2) * (p.ntx + 2) <= 1024
+    assert p.TH + 2 * p.k <= 16 * p.R and p.TH >= p.k
+    assert p.HB % 16 == 0 and p.HB >= p.k * c and p.TWB + 2 * p.HB == 512 and p.TWB >= p.HB
+    assert p.nty * p.TH >= rows and p.ntx * p.TWB >= cb
