@@ -69,9 +69,13 @@ __device__ __forceinline__ uint4 load_chunk(const pconv_geometry_t& g, const Sou
     return load_chunk_bytes(g, s, orow, lrow, gb);
 }
 
-// Load R consecutive rows of one 16-byte column strip (a warp's band) into registers. The column
-// classification (owner, offset, fast/slow) is done once; per row only the owning tile-row is
-// selected, so the common case costs a compare, a 64-bit multiply-add and one 128-bit load.
+// Load R consecutive rows of one 16-byte column strip (a warp's band) into registers. Everything
+// that does not depend on the row is hoisted: the column classification (owner, offset, fast/slow),
+// the address of band row 0 in each of the three owning tile-rows' buffers, and the band-relative
+// 32-bit row ranges (inside the image / owned by tile-row 0, 1, 2). Per row that leaves two 32-bit
+// compares, a pointer select, one 32x32+64 multiply-add and one 128-bit load — the region load is
+// executed by every thread of every launch, so its instruction count is launch overhead.
+// (Pitches are < 2^31: checked by the launchers.)
 template <int R, bool MASKED = false>
 __device__ __forceinline__ void load_band(uint4 (&rows)[R], const pconv_geometry_t& g,
                                           const SourceSet& s, int64_t gr0, int64_t gb,
@@ -81,27 +85,49 @@ __device__ __forceinline__ void load_band(uint4 (&rows)[R], const pconv_geometry
     const bool col_whole = gb >= 0 && gb + 16 <= g.img_cb;
     const int oc = owner_of(gb < 0 ? 0 : gb, g.cb_lo);
     const bool one_owner = col_whole && owner_of(gb + 15, g.cb_lo) == oc;
-    // Per owning tile-row (scalars, never indexed dynamically -> they stay in registers): pointer to
-    // (image row 0 of that tile, my column), its pitch, and whether 128-bit loads are legal there.
-    const int64_t p0 = s.pitch[oc], p1 = s.pitch[3 + oc], p2 = s.pitch[6 + oc];
     const int64_t cofs = gb - g.cb_lo[oc];
-    const uint8_t* b0 = s.p[oc] ? s.p[oc] + cofs - g.row_lo[0] * p0 : nullptr;
-    const uint8_t* b1 = s.p[3 + oc] ? s.p[3 + oc] + cofs - g.row_lo[1] * p1 : nullptr;
-    const uint8_t* b2 = s.p[6 + oc] ? s.p[6 + oc] + cofs - g.row_lo[2] * p2 : nullptr;
-    const bool f0 = one_owner && b0 && ((reinterpret_cast<uintptr_t>(b0) | (uintptr_t)p0) & 15u) == 0;
-    const bool f1 = one_owner && b1 && ((reinterpret_cast<uintptr_t>(b1) | (uintptr_t)p1) & 15u) == 0;
-    const bool f2 = one_owner && b2 && ((reinterpret_cast<uintptr_t>(b2) | (uintptr_t)p2) & 15u) == 0;
+    // band-relative row boundaries, clamped to [0, R]
+    auto rel = [&](int64_t v) { v -= gr0; return (int)(v < 0 ? 0 : (v > R ? R : v)); };
+    const int i_lo = rel(0), i_hi = rel(g.img_rows);            // rows inside the image
+    const int n1 = rel(g.row_lo[1]), n2 = rel(g.row_lo[2]);     // tile-row 0 below n1, 1 below n2, else 2
+    // address of (image row gr0, my column) in the buffer of owning tile-row o, and whether 128-bit
+    // loads are legal there
+    auto origin = [&](int o, int& pitch, bool& fast) -> const uint8_t* {
+        pitch = (int)s.pitch[3 * o + oc];
+        const uint8_t* base = s.p[3 * o + oc];
+        const uint8_t* a = base ? base + cofs + (gr0 - g.row_lo[o]) * pitch : nullptr;
+        fast = one_owner && a && ((reinterpret_cast<uintptr_t>(a) | (uintptr_t)pitch) & 15u) == 0;
+        return a;
+    };
+    // Common case first (warp-uniform except for the alignment test): the whole band lies inside the
+    // image and inside ONE owning tile-row — per row a multiply-add and a 128-bit load.
+    if (i_lo == 0 && i_hi == R && !col_out && (n1 == R || (n1 == 0 && n2 == R) || n2 == 0)) {
+        int pitch;
+        bool fast;
+        const uint8_t* a = origin(n1 == R ? 0 : (n2 == R ? 1 : 2), pitch, fast);
+        if (fast) {
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                if (!MASKED || ((mask >> i) & 1u))
+                    rows[i] = __ldcg(reinterpret_cast<const uint4*>(a + (int64_t)i * pitch));
+            return;
+        }
+    }
+    int p0, p1, p2;
+    bool f0, f1, f2;
+    const uint8_t* a0 = origin(0, p0, f0);
+    const uint8_t* a1 = origin(1, p1, f1);
+    const uint8_t* a2 = origin(2, p2, f2);
     uint32_t slow = 0;   // rows that need the byte-wise path (rare: odd tile widths, image edge)
 #pragma unroll
     for (int i = 0; i < R; ++i) {
         if (MASKED && !((mask >> i) & 1u)) continue;   // keep this row (resident halo refresh)
-        const int64_t gr = gr0 + i;
-        if (col_out || gr < 0 || gr >= g.img_rows) { rows[i] = z; continue; }
-        const bool in0 = gr < g.row_lo[1], in1 = gr < g.row_lo[2];
-        const uint8_t* base = in0 ? b0 : (in1 ? b1 : b2);
-        const int64_t pitch = in0 ? p0 : (in1 ? p1 : p2);
+        if (col_out || i < i_lo || i >= i_hi) { rows[i] = z; continue; }
+        const bool in0 = i < n1, in1 = i < n2;
+        const uint8_t* a = in0 ? a0 : (in1 ? a1 : a2);
+        const int pitch = in0 ? p0 : (in1 ? p1 : p2);
         const bool fast = in0 ? f0 : (in1 ? f1 : f2);
-        if (fast) rows[i] = __ldcg(reinterpret_cast<const uint4*>(base + gr * pitch));
+        if (fast) rows[i] = __ldcg(reinterpret_cast<const uint4*>(a + (int64_t)i * pitch));
         else slow |= 1u << i;
     }
     if (slow) {
@@ -115,24 +141,17 @@ __device__ __forceinline__ void load_band(uint4 (&rows)[R], const pconv_geometry
     }
 }
 
-// Store one 16-byte chunk at image position (gr, gb) into my tile, clipped to the tile.
-__device__ __forceinline__ void store_chunk(uint8_t* __restrict__ dst, const pconv_geometry_t& g,
-                                            int64_t gr, int64_t gb, const uint4& v) {
-    const int64_t lr = gr - g.row_lo[1], lb = gb - g.cb_lo[1];
-    const int64_t tile_rows = g.row_lo[2] - g.row_lo[1], tile_cb = g.cb_lo[2] - g.cb_lo[1];
-    if (lr < 0 || lr >= tile_rows || lb + 16 <= 0 || lb >= tile_cb) return;
-    uint8_t* a = dst + lr * g.pitch + lb;
-    if (lb >= 0 && lb + 16 <= tile_cb && (reinterpret_cast<uintptr_t>(a) & 15u) == 0) {
-        __stcg(reinterpret_cast<uint4*>(a), v);
-    } else {
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        for (int t = 0; t < 16; ++t)
-            if (lb + t >= 0 && lb + t < tile_cb) a[t] = (uint8_t)(w[t >> 2] >> (8 * (t & 3)));
-    }
+// Slow path of store_band: a chunk that straddles the tile edge or is misaligned goes out byte by
+// byte. Out of line for the same reason as load_chunk_bytes.
+static __device__ __noinline__ void store_chunk_bytes(uint8_t* a, int64_t lb, int64_t tile_cb, uint4 v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    for (int t = 0; t < 16; ++t)
+        if (lb + t >= 0 && lb + t < tile_cb) a[t] = (uint8_t)(w[t >> 2] >> (8 * (t & 3)));
 }
 
-// Store the rows of a band selected by `mask` (bit i = row i) into my tile; the column test and the
-// address arithmetic are hoisted out of the row loop.
+// Store the rows of a band selected by `mask` (bit i = row i) into my tile, clipped to the tile. The
+// column test, the row clipping (as a bit range) and the address of band row 0 are hoisted out of the
+// row loop; per selected row: one multiply-add and one 128-bit store.
 template <int R>
 __device__ __forceinline__ void store_band(const uint4 (&rows)[R], uint32_t mask,
                                            uint8_t* __restrict__ dst, const pconv_geometry_t& g,
@@ -140,21 +159,31 @@ __device__ __forceinline__ void store_band(const uint4 (&rows)[R], uint32_t mask
     const int64_t lb = gb - g.cb_lo[1], lr0 = gr0 - g.row_lo[1];
     const int64_t tile_rows = g.row_lo[2] - g.row_lo[1], tile_cb = g.cb_lo[2] - g.cb_lo[1];
     if (mask == 0u || lb + 16 <= 0 || lb >= tile_cb) return;
+    // band rows [i_lo, i_hi) lie inside the tile
+    const int i_lo = (int)(lr0 < 0 ? (lr0 < -R ? R : -lr0) : 0);
+    const int64_t left = tile_rows - lr0;
+    const int i_hi = (int)(left < 0 ? 0 : (left > R ? R : left));
+    if (i_lo >= i_hi) return;
+    const uint32_t range = (i_hi >= 32 ? 0xffffffffu : ((1u << i_hi) - 1u)) & ~((1u << i_lo) - 1u);
+    const uint32_t m = mask & range;
+    const int pitch = (int)g.pitch;
     uint8_t* a0 = dst + lr0 * g.pitch + lb;
     const bool fast = lb >= 0 && lb + 16 <= tile_cb && (reinterpret_cast<uintptr_t>(a0) & 15u) == 0 &&
-                      (g.pitch & 15) == 0;
+                      (pitch & 15) == 0;
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-        if (!((mask >> i) & 1u)) continue;
-        const int64_t lr = lr0 + i;
-        if (lr < 0 || lr >= tile_rows) continue;
-        if (fast) __stcg(reinterpret_cast<uint4*>(a0 + i * g.pitch), rows[i]);
-        else store_chunk(dst, g, gr0 + i, gb, rows[i]);
+        if (!((m >> i) & 1u)) continue;
+        uint8_t* a = a0 + (int64_t)i * pitch;
+        if (fast) __stcg(reinterpret_cast<uint4*>(a), rows[i]);
+        else store_chunk_bytes(a, lb, tile_cb, rows[i]);
     }
 }
 
-// Byte mask of a lane's 16-byte strip: 0xff where the byte lies inside the image.
+// Byte mask of a lane's 16-byte strip: 0xff where the byte lies inside the image. Only CTAs whose
+// region sticks out of the image sideways (*need, CTA-uniform) pay for the per-byte classification.
 __device__ __forceinline__ uint4 column_mask(const pconv_geometry_t& g, int64_t gb0, bool* need) {
+    *need = (gb0 < 0) || (gb0 + kSP > g.img_cb);
+    if (!*need) return make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     const int64_t gb = gb0 + 16 * (threadIdx.x & 31);
     uint32_t m[4];
 #pragma unroll
@@ -167,7 +196,6 @@ __device__ __forceinline__ uint4 column_mask(const pconv_geometry_t& g, int64_t 
         }
         m[j] = w;
     }
-    *need = (gb0 < 0) || (gb0 + kSP > g.img_cb);  // CTA-uniform
     return make_uint4(m[0], m[1], m[2], m[3]);
 }
 

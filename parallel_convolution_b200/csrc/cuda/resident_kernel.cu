@@ -64,6 +64,7 @@ extern "C" int pconv_resident_launch(const pconv_resident_params_t* p, void* str
     const int64_t tile_rows = g.row_lo[2] - g.row_lo[1], tile_cb = g.cb_lo[2] - g.cb_lo[1];
     if ((int64_t)p->nty * p->TH < tile_rows || (int64_t)p->ntx * p->TWB < tile_cb)
         return pconv_rt::fail("CTA grid does not cover the tile");
+    if (g.pitch <= 0 || g.pitch >= ((int64_t)1 << 30)) return pconv_rt::fail("tile pitch out of range");
     const bool dual = p->dual != 0;   // split-phase: nty counts virtual tile rows, two per CTA
     if (dual && (p->nty & 1)) return pconv_rt::fail("split-phase resident kernel needs an even number of tile rows");
     if ((int64_t)(p->nty + 2) * (p->ntx + 2) > 1024) return pconv_rt::fail("CTA flag grid exceeds its 4 KB pad");

@@ -76,6 +76,10 @@ extern "C" int pconv_stream_launch(const pconv_stream_params_t* p, void* stream)
         return pconv_rt::fail("bad region geometry (k/TH/TWB/HB/R)");
     const int64_t tile_rows = g.row_lo[2] - g.row_lo[1], tile_cb = g.cb_lo[2] - g.cb_lo[1];
     if (tile_rows <= 0 || tile_cb <= 0) return pconv_rt::fail("empty tile");
+    constexpr int64_t kMaxPitch = (int64_t)1 << 30;   // region_io.cuh does 32-bit row * pitch products
+    if (g.pitch <= 0 || g.pitch >= kMaxPitch) return pconv_rt::fail("tile pitch out of range");
+    for (int d = 0; d < 9; ++d)
+        if (p->src_pitch[d] < 0 || p->src_pitch[d] >= kMaxPitch) return pconv_rt::fail("source pitch out of range");
     // the halo may only reach into the *adjacent* tiles
     for (int s = 0; s < 3; s += 2) {
         const int64_t nr = g.row_lo[s + 1] - g.row_lo[s], nc = g.cb_lo[s + 1] - g.cb_lo[s];
