@@ -40,8 +40,8 @@ def programs(nty, ntx, nblocks):
     return progs
 
 
-def main():
-    GR, GC, nty, ntx, nblocks = (int(v) for v in sys.argv[1:6])
+def simulate(GR, GC, nty, ntx, nblocks):
+    """Run every CTA of a GR x GC rank grid to completion; returns the blocked (rank, cta, op) list."""
     fw = ntx + 2
     flags = {(r, c): [0] * ((nty + 2) * fw) for r in range(GR) for c in range(GC)}
     progs = {(r, c): programs(nty, ntx, nblocks) for r in range(GR) for c in range(GC)}
@@ -90,13 +90,18 @@ def main():
                 i += 1
                 progress = True
             pc[(rk, cta)] = i
-    stuck = [(rk, cta, progs[rk][cta][i]) for (rk, cta), i in pc.items() if i < len(progs[rk][cta])]
+    return [(rk, cta, progs[rk][cta][i], ready(rk, cta[1], *progs[rk][cta][i][1:4])[1])
+            for (rk, cta), i in pc.items() if i < len(progs[rk][cta])]
+
+
+def main():
+    GR, GC, nty, ntx, nblocks = (int(v) for v in sys.argv[1:6])
+    stuck = simulate(GR, GC, nty, ntx, nblocks)
     if not stuck:
         print("OK: every CTA ran to completion")
         return 0
     print(f"DEADLOCK: {len(stuck)} CTAs blocked")
-    for rk, cta, op in stuck[:12]:
-        ok, why = ready(rk, cta[1], op[1], op[2], op[3])
+    for rk, cta, op, why in stuck[:12]:
         print(f"  rank {rk} cta {cta}: {op} blocked on dir/ei/ej {why}")
     return 1
 

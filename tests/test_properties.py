@@ -90,3 +90,18 @@ def test_split_phase_plans_are_launchable(rows, cb, c, kind, loops, sms):
     assert p.TH + 2 * p.k <= 16 * p.R and p.TH >= p.k
     assert p.HB % 16 == 0 and p.HB >= p.k * c and p.TWB + 2 * p.HB == 512 and p.TWB >= p.HB
     assert p.nty * p.TH >= rows and p.ntx * p.TWB >= cb
+
+
+@settings(max_examples=60, deadline=None)
+@given(gr=st.integers(1, 3), gc=st.integers(1, 3), half_rows=st.integers(1, 5), ntx=st.integers(1, 4),
+       nblocks=st.integers(1, 5))
+def test_split_phase_flag_protocol_never_deadlocks(gr, gc, half_rows, ntx, nblocks):
+    """Replay of the split-phase resident kernel's wait/publish program (scripts/sim_split_phase.py mirrors
+    resident2_kernel.cuh): for any rank grid and CTA grid every CTA must run to completion."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "sim_split_phase.py")
+    spec = importlib.util.spec_from_file_location("sim_split_phase", path)
+    sim = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sim)
+    assert sim.simulate(gr, gc, 2 * half_rows, ntx, nblocks) == []
