@@ -18,6 +18,9 @@
 #include <cstring>
 #include <vector>
 
+#include <cstdio>
+#include <string>
+
 #include "pconv_host.h"
 
 #define PCONV_CLONES __attribute__((target_clones("default", "avx2", "arch=x86-64-v4")))
@@ -176,6 +179,60 @@ extern "C" int pconv_cpu_run_image_blocked(const uint8_t* src, uint8_t* dst, int
         return 0;
     }
     return run_image_blocked(src, dst, H, W, C, f, loops, threads, k);
+}
+
+// Out-of-core: the image never has to fit in memory. Each pass streams the file through row strips
+// (strip + k-row halo, two ping-pong buffers sized by `mem_bytes`), advances a strip k iterations
+// (same staleness argument as the temporal blocking above) and writes it to the other file of a
+// ping-pong pair; ceil(loops/k) passes over the data in total. The reference cannot even address a
+// 32768x32768 RGB image (32-bit offsets, mpi/mpi_conv.c:120,142); this path only needs disk space.
+// Intermediate passes go to "<out>.pass" and the last one lands in `out_path`.
+extern "C" int pconv_cpu_run_file(const char* in_path, const char* out_path, int64_t H, int64_t W,
+                                  int C, const pconv_filter_t* f, int loops, int threads, int k,
+                                  int64_t mem_bytes) {
+    if (!in_path || !out_path || !f || H <= 0 || W <= 0 || C <= 0 || loops < 0) return -1;
+    if (std::strcmp(in_path, out_path) == 0) return -22;   // -EINVAL: strips are written while others are still unread
+    const int64_t rb = W * (int64_t)C;
+    if (pconv_file_size(in_path) < H * rb) return -5;   // -EIO: short input
+    const int64_t pitch = ((rb + 2 * C + 63) / 64) * 64;
+    if (k < 1) k = 8;
+    k = std::max(1, std::min(k, std::max(loops, 1)));
+    // strip height from the memory budget: two buffers of (strip + 2k + 2) rows
+    int64_t strip = (mem_bytes > 0 ? mem_bytes : ((int64_t)256 << 20)) / (2 * pitch) - 2 * k - 2;
+    if (strip < 4 * k) strip = 4 * k;                   // never let the halo dominate
+    strip = std::min(strip, H);
+    const int npass = loops == 0 ? 1 : (loops + k - 1) / k;
+    const std::string tmp = std::string(out_path) + ".pass";
+    std::vector<uint8_t> la((size_t)((strip + 2 * k + 2) * pitch)), lb(la.size());
+    int rc = pconv_create_file(out_path, H * rb);
+    if (rc == 0 && npass > 1) rc = pconv_create_file(tmp.c_str(), H * rb);
+    for (int pass = 0, done = 0; pass < npass && rc == 0; ++pass) {
+        const int kk = loops == 0 ? 0 : std::min(k, loops - done);
+        // the last pass must land in out_path: passes alternate backwards from there
+        const bool to_out = ((npass - 1 - pass) & 1) == 0;
+        const char* src_path = pass == 0 ? in_path : (to_out ? tmp.c_str() : out_path);
+        const char* dst_path = to_out ? out_path : tmp.c_str();
+        for (int64_t r0 = 0; r0 < H && rc == 0; r0 += strip) {
+            const int64_t r1 = std::min(H, r0 + strip);
+            const int64_t lo = std::max<int64_t>(0, r0 - kk), hi = std::min(H, r1 + kk);
+            const int64_t rows = hi - lo;
+            std::memset(la.data(), 0, (size_t)((rows + 2) * pitch));
+            std::memset(lb.data(), 0, (size_t)((rows + 2) * pitch));
+            uint8_t* xa = la.data() + pitch + C;   // local pixel (0,0) == image row lo
+            uint8_t* xb = lb.data() + pitch + C;
+            rc = pconv_read_rect(src_path, rb, lo, rows, 0, rb, xa, pitch);
+            if (rc != 0) break;
+            for (int j = 1; j <= kk; ++j) {
+                const int64_t a = lo > 0 ? j : 0, e = hi < H ? rows - j : rows;
+                pconv_cpu_convolve(xa, xb, pitch, C, f, a, e, 0, W, threads);
+                std::swap(xa, xb);
+            }
+            rc = pconv_write_rect(dst_path, rb, r0, r1 - r0, 0, rb, xa + (r0 - lo) * pitch, pitch);
+        }
+        done += kk;
+    }
+    if (npass > 1) std::remove(tmp.c_str());
+    return rc;
 }
 
 extern "C" int pconv_cpu_run_image(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,

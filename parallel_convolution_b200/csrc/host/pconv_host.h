@@ -67,6 +67,11 @@ int pconv_cpu_run_image(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, 
 // (pconv_cpu_run_image picks this automatically for memory-bound sizes).
 int pconv_cpu_run_image_blocked(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
                                 const pconv_filter_t* f, int loops, int threads, int k);
+// Out-of-core: file -> file, `loops` iterations, never holding more than ~mem_bytes of the image
+// (row strips with k-deep halos, ceil(loops/k) passes; intermediate passes use "<out>.pass").
+// k <= 0 / mem_bytes <= 0 pick defaults (8 iterations per pass, 256 MiB). 0 or -errno.
+int pconv_cpu_run_file(const char* in_path, const char* out_path, int64_t H, int64_t W, int C,
+                       const pconv_filter_t* f, int loops, int threads, int k, int64_t mem_bytes);
 int pconv_omp_max_threads(void);
 
 // ---- raw image I/O (64-bit offsets; reference: MPI_File_* mpi/mpi_conv.c:133-147,253-271) ----

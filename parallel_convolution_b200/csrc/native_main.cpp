@@ -1,7 +1,8 @@
 // pconv_native — stand-alone native CLI (no Python): the drop-in for the reference's ./cuda_conv
 // (cuda/main.c:10-55) on one B200, with a native CPU fallback (--cpu) for GPU-less boxes.
 //
-//   pconv_native image width height loops {rgb|grey} [--filter NAME] [--cpu] [--threads T] [-o OUT]
+//   pconv_native image width height loops {rgb|grey} [--filter NAME] [--cpu] [--threads T]
+//                [--out-of-core MiB] [-o OUT]
 //
 // Same positional grammar and the same "Execution time: %.3f sec" line (whole program: file read,
 // H2D, kernels, D2H, file write — cuda/main.c:20,48-50), plus the loop-only seconds on a second
@@ -29,7 +30,7 @@ const Builtin kBuiltins[] = {
 
 int usage(const char* prog) {
     std::fprintf(stderr, "Error Input!\n%s image_name width height loops [rgb/grey] "
-                         "[--filter NAME] [--cpu] [--threads T] [-o OUT]\n", prog);
+                         "[--filter NAME] [--cpu] [--threads T] [--out-of-core MiB] [-o OUT]\n", prog);
     return EXIT_FAILURE;
 }
 
@@ -59,10 +60,12 @@ int main(int argc, char** argv) {
     std::string filter = "gaussian", out;
     bool cpu = false;
     int threads = 0;
+    long long ooc_mib = 0;   // > 0: stream the file through the CPU engine without loading it
     for (int i = 6; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--filter") && i + 1 < argc) filter = argv[++i];
         else if (!std::strcmp(argv[i], "--cpu")) cpu = true;
         else if (!std::strcmp(argv[i], "--threads") && i + 1 < argc) threads = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--out-of-core") && i + 1 < argc) ooc_mib = std::atoll(argv[++i]);
         else if (!std::strcmp(argv[i], "-o") && i + 1 < argc) out = argv[++i];
         else return usage(argv[0]);
     }
@@ -84,6 +87,13 @@ int main(int argc, char** argv) {
     if (pconv_file_size(image.c_str()) < nbytes) {
         std::fprintf(stderr, "pconv_native: %s is shorter than %lld bytes\n", image.c_str(), (long long)nbytes);
         return EXIT_FAILURE;
+    }
+    if (ooc_mib > 0) {   // images larger than memory: file -> file through row strips (cpu_engine.cpp)
+        const double t0 = now_s();
+        const int rc = pconv_cpu_run_file(image.c_str(), out.c_str(), H, W, C, &f, loops, threads, 0, ooc_mib << 20);
+        if (rc != 0) { std::fprintf(stderr, "pconv_native: out-of-core run failed (%d)\n", rc); return EXIT_FAILURE; }
+        std::printf("%f\n", now_s() - t0);
+        return EXIT_SUCCESS;
     }
     std::vector<uint8_t> host((size_t)nbytes), result((size_t)nbytes);
     if (pconv_read_rect(image.c_str(), rb, 0, H, 0, rb, host.data(), rb) != 0) {

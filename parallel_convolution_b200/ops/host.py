@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
     L.pconv_cpu_convolve.argtypes = [u8p, u8p, i64, C.c_int, fsp, i64, i64, i64, i64, C.c_int]
     L.pconv_cpu_run_image.argtypes = [u8p, u8p, i64, i64, C.c_int, fsp, C.c_int, C.c_int]
     L.pconv_cpu_run_image_blocked.argtypes = [u8p, u8p, i64, i64, C.c_int, fsp, C.c_int, C.c_int, C.c_int]
+    L.pconv_cpu_run_file.argtypes = [C.c_char_p, C.c_char_p, i64, i64, C.c_int, fsp, C.c_int, C.c_int, C.c_int, i64]
     L.pconv_file_size.argtypes = [C.c_char_p]
     L.pconv_file_size.restype = i64
     L.pconv_read_rect.argtypes = [C.c_char_p, i64, i64, i64, i64, i64, u8p, i64]
@@ -165,6 +166,17 @@ def cpu_run_image_blocked(image: np.ndarray, f: FilterSpec, loops: int, k: int, 
     if rc != 0:
         raise RuntimeError(f"blocked cpu engine failed ({rc})")
     return out
+
+
+def cpu_run_file(path_in: str, path_out: str, height: int, width: int, Cn: int, f: FilterSpec, loops: int,
+                 threads: int = 0, k: int = 0, mem_bytes: int = 0) -> None:
+    """Out-of-core file -> file run of the native CPU engine: row strips with k-deep halos,
+    ceil(loops/k) passes, at most ~``mem_bytes`` of the image in memory. Bit-identical to the oracle."""
+    rc = lib().pconv_cpu_run_file(os.fsencode(path_in), os.fsencode(path_out), height, width, Cn,
+                                  C.byref(f), loops, threads, k, mem_bytes)
+    if rc != 0:
+        raise OSError(-rc if rc < 0 else rc, f"out-of-core run failed ({os.strerror(-rc) if rc < 0 else rc}): "
+                                             f"{path_in} -> {path_out}")
 
 
 def cpu_convolve(src: np.ndarray, dst: np.ndarray, halo: int, Cn: int, f: FilterSpec,

@@ -108,3 +108,31 @@ def test_np_flag_spawns_ranks_like_mpirun(raw):
     assert rep["workers"] == 2
     got = np.fromfile(p.parent / ("blur_" + p.name), dtype=np.uint8).reshape(40, 56)
     assert np.array_equal(got, host.oracle(img, Filter.builtin("gaussian").spec, 5))
+
+
+def test_out_of_core_file_run_matches_oracle(tmp_path):
+    """--out-of-core: strips + k-deep halos + several passes over ping-pong files == the oracle."""
+    rng = np.random.default_rng(23)
+    img = rng.integers(0, 256, (300, 67, 3), dtype=np.uint8)
+    src = tmp_path / "big.raw"
+    img.tofile(src)
+    ref = host.oracle(img, Filter.builtin("sharpen").spec, 11)
+    # direct binding: tiny memory budget -> many strips; k=4 -> 3 passes (4+4+3)
+    out = tmp_path / "o1.raw"
+    host.cpu_run_file(str(src), str(out), 300, 67, 3, Filter.builtin("sharpen").spec, 11, k=4, mem_bytes=40_000)
+    assert np.array_equal(np.fromfile(out, dtype=np.uint8).reshape(img.shape), ref)
+    assert not os.path.exists(str(out) + ".pass")
+    # CLI, default k, even number of passes, grey
+    g = rng.integers(0, 256, (257, 130), dtype=np.uint8)
+    gs = tmp_path / "g.raw"
+    g.tofile(gs)
+    r = run_cli(gs, 130, 257, 16, "grey", "--backend", "cpu", "--out-of-core", 1, "--json", "-o", tmp_path / "o2.raw")
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout)["backend"].startswith("cpu")
+    got = np.fromfile(tmp_path / "o2.raw", dtype=np.uint8).reshape(g.shape)
+    assert np.array_equal(got, host.oracle(g, Filter.builtin("gaussian").spec, 16))
+    # loops = 0 copies; in == out is refused
+    host.cpu_run_file(str(gs), str(tmp_path / "o3.raw"), 257, 130, 1, Filter.builtin("box").spec, 0)
+    assert np.array_equal(np.fromfile(tmp_path / "o3.raw", dtype=np.uint8).reshape(g.shape), g)
+    with pytest.raises(OSError):
+        host.cpu_run_file(str(gs), str(gs), 257, 130, 1, Filter.builtin("box").spec, 3)
