@@ -1,5 +1,7 @@
+# One-GPU check used during kernel work: full GPU test suite, the three kernel modes on 1 and 8 virtual
+# ranks (quick_bench), the per-launch cost fit, and the headline bench. Output: gpurun_out/modes/.
 set -u
-O=gpurun_out/io; mkdir -p $O
+O=gpurun_out/modes; mkdir -p $O
 timeout 1200 python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; echo "pytest rc=$? $(tail -1 $O/pytest_gpu.log)"
 for args in "--mode stream" "--mode resident" "--mode resident2" "--mode stream --workers 8" "--mode resident --workers 8" "--mode resident2 --workers 8"; do
   timeout 120 python scripts/quick_bench.py --loops 100 --reps 6 $args 2>&1 | tail -1 | cut -c1-700
