@@ -70,6 +70,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--resume", action="store_true", help="continue from the checkpoint of this output")
     p.add_argument("--verify", action="store_true",
                    help="recompute on the CPU oracle engine and compare byte for byte (small images)")
+    p.add_argument("--exact-ref", action="store_true",
+                   help="accepted for compatibility: every backend is ALWAYS bit-identical to the reference's "
+                        "single-process fp32 semantics (there is no approximate mode to switch off)")
     p.add_argument("--timeout-ms", type=float, default=10_000.0, help="in-kernel halo watchdog")
     p.add_argument("--inject-drop-signal", type=int, default=None, metavar="RANK",
                    help="fault injection: RANK never signals its neighbours (watchdog demo)")
