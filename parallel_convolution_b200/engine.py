@@ -373,6 +373,44 @@ class ConvEngine:
         self.iterate(loops)
         return self.gather()
 
+    def run_tensor(self, x, loops: int):
+        """PyTorch interface of the GPU backends: ``x`` is a uint8 CUDA tensor on this engine's device —
+        the whole image ``(H, W[, C])`` in a single process, this rank's tile ``(rows, cols[, C])``
+        under ``torch.distributed``. Returns a new tensor of the same shape holding the result of
+        ``loops`` iterations. Device to device: the data never visits the host."""
+        import torch
+        from .ops import cuda as K
+        if self.backend not in ("fused", "nccl"):
+            raise RuntimeError("run_tensor needs a GPU backend (fused or nccl)")
+        g, C = self.grid, self.grid.channels
+        tiles = list(self.local_tiles)
+        rows, cols = (tiles[0].rows, tiles[0].cols) if self.distributed else (g.height, g.width)
+        want = (rows, cols) if C == 1 else (rows, cols, C)
+        if (not isinstance(x, torch.Tensor) or x.dtype != torch.uint8 or not x.is_cuda
+                or tuple(x.shape) != want or x.device.index != self.device):
+            raise ValueError(f"expected a uint8 CUDA tensor of shape {want} on cuda:{self.device}")
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        rt = self._impl
+        src_pitch = cols * C
+        torch.cuda.current_stream(x.device).synchronize()     # x is complete; `out` is allocated
+        if hasattr(rt, "_barrier"):
+            rt._barrier()                                     # previous run's readers are done with my buffers
+        for t in tiles:
+            off = 0 if self.distributed else (t.row0 * g.width + t.col0) * C
+            K.memcpy2d_async(rt.mems[t.rank].bufs[0], rt.pitch, x.data_ptr() + off, src_pitch,
+                             t.cols * C, t.rows, K.D2D, rt.stream)
+        rt.parity = 0
+        if hasattr(rt, "slot"):
+            rt.slot = 0
+        self.iterate(loops)                                   # synchronises the runtime stream
+        for t in tiles:
+            off = 0 if self.distributed else (t.row0 * g.width + t.col0) * C
+            K.memcpy2d_async(out.data_ptr() + off, src_pitch, rt.mems[t.rank].bufs[rt.parity], rt.pitch,
+                             t.cols * C, t.rows, K.D2D, rt.stream)
+        K.stream_sync(rt.stream)
+        return out
+
     def run_batch(self, paths_in: list[str], loops: int, out_dir: str | None = None) -> dict:
         """Data-parallel-in-time batch mode: filter many images of the engine's shape.
 

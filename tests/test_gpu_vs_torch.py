@@ -55,3 +55,24 @@ def test_virtual_ranks_match_torch(rng):
     for mode in ("stream", "resident"):
         with ConvEngine(width=256, height=192, channels=3, filter=f, backend="fused", workers=4, mode=mode) as eng:
             assert np.array_equal(eng.run(img, 5), ref), mode
+
+
+def test_run_tensor_device_to_device(rng):
+    """ConvEngine.run_tensor: uint8 CUDA tensor in, uint8 CUDA tensor out, no host staging — on one tile
+    and on 4 virtual ranks, against the plain torch fp32 reference."""
+    import torch
+    from parallel_convolution_b200 import ConvEngine
+    for c, name in ((3, "gaussian"), (1, "sharpen")):
+        img = random_image(rng, 200, 264, c)
+        f = Filter.builtin(name)
+        ref = torch_reference(img, f.taps, 6, "cuda")
+        x = torch.from_numpy(img).cuda()
+        for workers in (1, 4):
+            with ConvEngine(width=264, height=200, channels=c, filter=f, backend="fused", workers=workers) as eng:
+                y = eng.run_tensor(x, 6)
+                assert y.is_cuda and y.dtype == torch.uint8 and y.shape == x.shape
+                assert np.array_equal(y.cpu().numpy(), ref), (c, name, workers)
+                y2 = eng.run_tensor(y, 0)                 # zero iterations: a copy
+                assert torch.equal(y2, y)
+                with pytest.raises(ValueError):
+                    eng.run_tensor(x.cpu(), 1)
