@@ -136,3 +136,18 @@ def test_out_of_core_file_run_matches_oracle(tmp_path):
     assert np.array_equal(np.fromfile(tmp_path / "o3.raw", dtype=np.uint8).reshape(g.shape), g)
     with pytest.raises(OSError):
         host.cpu_run_file(str(gs), str(gs), 257, 130, 1, Filter.builtin("box").spec, 3)
+
+
+def test_netpbm_round_trip(tmp_path):
+    from parallel_convolution_b200.utils import netpbm
+    rng = np.random.default_rng(2)
+    for c in (1, 3):
+        img = rng.integers(0, 256, (17, 23, c) if c == 3 else (17, 23), dtype=np.uint8)
+        raw, pnm, back = tmp_path / f"a{c}.raw", tmp_path / f"a{c}.pnm", tmp_path / f"b{c}.raw"
+        img.tofile(raw)
+        assert netpbm.main(["raw2pnm", str(raw), "23", "17", "rgb" if c == 3 else "grey", str(pnm)]) == 0
+        head = open(pnm, "rb").read(15)
+        assert head.startswith(b"P6\n23 17\n255\n" if c == 3 else b"P5\n23 17\n255\n")
+        assert netpbm.pnm_to_raw(str(pnm), str(back)) == (23, 17, c)
+        assert np.array_equal(np.fromfile(back, dtype=np.uint8), img.ravel())
+    assert netpbm.main(["raw2pnm", str(raw), "230", "170", "rgb", str(pnm)]) == 1   # short input
