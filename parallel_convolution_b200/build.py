@@ -42,7 +42,8 @@ HOST_ORACLE = "host/oracle.cpp"  # compiled separately at -O1 with contraction o
 CUDA_SOURCES = ["cuda/runtime.cu", "cuda/pack_kernels.cu", "cuda/stream_kernel.cu", "cuda/resident_kernel.cu",
                 "cuda/stream_kind_sep.cu", "cuda/stream_kind_int.cu", "cuda/stream_kind_f32.cu",
                 "cuda/resident_kind_sep.cu", "cuda/resident_kind_int.cu", "cuda/resident_kind_f32.cu",
-                "cuda/resident2_kind_sep.cu", "cuda/resident2_kind_int.cu", "cuda/resident2_kind_f32.cu"]
+                "cuda/resident2_kind_sep.cu", "cuda/resident2_kind_int.cu", "cuda/resident2_kind_f32.cu",
+                "cuda/resident3_kind_sep.cu", "cuda/resident3_kind_int.cu", "cuda/resident3_kind_f32.cu"]
 
 CXXFLAGS = ["-std=c++17", "-fPIC", "-O3", "-ffp-contract=off", "-fopenmp", "-Wall",
             "-Wno-unknown-pragmas"]

@@ -41,9 +41,10 @@ def build_parser() -> argparse.ArgumentParser:
                    help="builtin name (box, gaussian, edge, sharpen, laplacian, emboss, sobel_x, sobel_y, "
                         "identity), 'a,b,c,d,e,f,g,h,i[/div]', nine floats, or a file")
     p.add_argument("--backend", default="auto", choices=["auto", "fused", "nccl", "cpu", "host"])
-    p.add_argument("--mode", default="auto", choices=["auto", "stream", "resident", "resident2"],
+    p.add_argument("--mode", default="auto", choices=["auto", "stream", "resident", "resident2", "resident3"],
                    help="fused backend: streaming launches, the persistent on-chip kernel, or its "
-                        "split-phase variant (exchange overlapped with arithmetic)")
+                        "split-phase variant (exchange overlapped with arithmetic); resident3 = split-phase "
+                        "with a protocol warp (experimental)")
     p.add_argument("--gpus", "--workers", dest="workers", type=int, default=None,
                    help="single process: decompose over N virtual ranks on one GPU")
     p.add_argument("-np", "--np", dest="nprocs", type=int, default=None, metavar="N",

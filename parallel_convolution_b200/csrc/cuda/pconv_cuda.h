@@ -75,7 +75,7 @@ int pconv_stream_run(const pconv_stream_params_t* pp, int nranks, const int32_t*
 int pconv_sync_launch(const pconv_sync_t* s, void* stream);
 // Force the lazy module load of the kernel a plan will use (cudaFuncGetAttributes), so that the
 // first timed run does not pay ~10 ms of one-time SASS loading. resident: 0 stream kernel,
-// 1 resident kernel, 2 split-phase resident kernel.
+// 1 resident kernel, 2 split-phase resident kernel, 3 split-phase + protocol warp (experimental).
 int pconv_kernel_prepare(int kind, int C, int R, int resident);
 // Band heights compiled for a filter kind; returns the count, fills out[0..cap).
 int pconv_stream_band_heights(int kind, int* out, int cap);
@@ -101,13 +101,15 @@ typedef struct pconv_resident_params {
     uint32_t* cta_flags;     // [(nty+2)*(ntx+2)] epochs, incl. a ring mirrored from neighbour GPUs
     uint32_t* remote_cta_flags[9];  // the same array on neighbour d (peer-mapped) or NULL
     uint32_t epoch_base;     // exchange b (1-based) uses epoch_base + b; host advances it per run
-    uint32_t dual;           // 1: split-phase kernel (two virtual tile rows per CTA, nty counts them; even)
+    uint32_t dual;           // 1: split-phase kernel (two virtual tile rows per CTA, nty counts them; even);
+                             // 2: the same with a protocol warp (resident3_kernel.cuh, experimental)
     pconv_sync_t sync;       // launch-level protocol, identical to the stream kernel's
 } pconv_resident_params_t;
 // The result lands in parity (ceil(loops/k) & 1): 1 -> self_b, 0 -> self_a.
 int pconv_resident_launch(const pconv_resident_params_t* p, void* stream);
 // Band heights (rows per warp per virtual tile) compiled for the split-phase kernel.
 int pconv_resident2_band_heights(int kind, int* out, int cap);
+int pconv_resident3_band_heights(int kind, int* out, int cap);
 
 // ---- runtime -----------------------------------------------------------------------------------
 int pconv_cuda_device_count(void);

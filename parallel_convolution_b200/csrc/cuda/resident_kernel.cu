@@ -37,15 +37,20 @@
 #include <cstring>
 
 #include "resident2_kernel.cuh"
+#include "resident3_kernel.cuh"
 #include "resident_kernel.cuh"
 
 namespace pconv {
 
-static ResidentFn pick_kernel(int kind, int C, int R, bool dual = false) {
+// variant: 0 single-phase, 1 split-phase (resident2), 2 split-phase + protocol warp (resident3)
+static ResidentFn pick_kernel(int kind, int C, int R, int variant = 0) {
     switch (kind) {
-        case PCONV_KIND_SEP121: return dual ? pick_resident2_sep(C, R) : pick_resident_sep(C, R);
-        case PCONV_KIND_INT: return dual ? pick_resident2_int(C, R) : pick_resident_int(C, R);
-        case PCONV_KIND_F32: return dual ? pick_resident2_f32(C, R) : pick_resident_f32(C, R);
+        case PCONV_KIND_SEP121:
+            return variant == 2 ? pick_resident3_sep(C, R) : variant == 1 ? pick_resident2_sep(C, R) : pick_resident_sep(C, R);
+        case PCONV_KIND_INT:
+            return variant == 2 ? pick_resident3_int(C, R) : variant == 1 ? pick_resident2_int(C, R) : pick_resident_int(C, R);
+        case PCONV_KIND_F32:
+            return variant == 2 ? pick_resident3_f32(C, R) : variant == 1 ? pick_resident2_f32(C, R) : pick_resident_f32(C, R);
         default: return nullptr;
     }
 }
@@ -58,8 +63,8 @@ extern "C" int pconv_resident_launch(const pconv_resident_params_t* p, void* str
     if (!p) return pconv_rt::fail("null params");
     const pconv_geometry_t& g = p->g;
     if (p->loops < 1 || p->k < 1 || p->TH < 1 || p->TWB < 16 || (p->TWB & 15) || (p->HB & 15) ||
-        p->HB < p->k * g.C || p->TWB + 2 * p->HB > kSP || p->TH + 2 * p->k > kWarps * p->R ||
-        p->TH < p->k || p->TWB < p->HB)
+        p->HB < p->k * g.C || p->TWB + 2 * p->HB > kSP ||
+        p->TH + 2 * p->k > (p->dual == 2 ? kCompWarps : kWarps) * p->R || p->TH < p->k || p->TWB < p->HB)
         return pconv_rt::fail("bad resident geometry (loops/k/TH/TWB/HB/R)");
     const int64_t tile_rows = g.row_lo[2] - g.row_lo[1], tile_cb = g.cb_lo[2] - g.cb_lo[1];
     if ((int64_t)p->nty * p->TH < tile_rows || (int64_t)p->ntx * p->TWB < tile_cb)
@@ -80,7 +85,7 @@ extern "C" int pconv_resident_launch(const pconv_resident_params_t* p, void* str
         return pconv_rt::fail("last CTA row is shallower than the halo and a rank lies below");
     if (g.cb_lo[3] > g.cb_lo[2] && tile_cb - (int64_t)(p->ntx - 1) * p->TWB < (int64_t)p->k * g.C)
         return pconv_rt::fail("last CTA column is narrower than the halo and a rank lies to the right");
-    ResidentFn fn = pick_kernel(p->filt.kind, g.C, p->R, dual);
+    ResidentFn fn = pick_kernel(p->filt.kind, g.C, p->R, (int)p->dual);
     if (!fn) return pconv_rt::fail("unsupported (filter kind, channels, band height) combination");
 
     ResidentArgs a;
@@ -118,8 +123,18 @@ extern "C" int pconv_resident2_band_heights(int kind, int* out, int cap) {
     return n;
 }
 
-extern "C" int pconv_resident_prepare(int kind, int C, int R, int dual) {
-    ResidentFn fn = pick_kernel(kind, C, R, dual != 0);
+extern "C" int pconv_resident3_band_heights(int kind, int* out, int cap) {
+    int n = 0;
+#define PUSH(RR) if (n < cap) out[n] = RR; ++n;
+    if (kind == PCONV_KIND_F32) { PCONV_RES3_R_F32(PUSH) }
+    else if (kind == PCONV_KIND_INT) { PCONV_RES3_R_INT(PUSH) }
+    else { PCONV_RES3_R_SEP(PUSH) }
+#undef PUSH
+    return n;
+}
+
+extern "C" int pconv_resident_prepare(int kind, int C, int R, int variant) {
+    ResidentFn fn = pick_kernel(kind, C, R, variant);
     if (!fn) return pconv_rt::fail("unsupported (filter kind, channels, band height) combination");
     cudaFuncAttributes at;
     cudaError_t e = cudaFuncGetAttributes(&at, (const void*)fn);

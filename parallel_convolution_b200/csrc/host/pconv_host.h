@@ -38,7 +38,8 @@ typedef struct pconv_plan_request {
     int32_t force_k, force_R;       // 0: planner decides
     int32_t resident;               // 1: plan the persistent resident kernel (all CTAs co-resident)
     int32_t peers;                  // 1: neighbours sit on other GPUs (dearer exchanges)
-    int32_t dual;                   // resident only: 1 = split-phase kernel, two virtual tile rows per CTA
+    int32_t dual;                   // resident only: 1 = split-phase kernel, two virtual tile rows per CTA;
+                                    // 2 = the same with a protocol warp (regions are 15*R rows)
 } pconv_plan_request_t;
 typedef struct pconv_plan_result {
     int32_t k, R, TH, TWB, HB, ntx, nty, waves;

@@ -41,12 +41,13 @@ extern "C" int pconv_plan(const pconv_plan_request_t* q, pconv_plan_t* out) {
     const double rate = bytes_per_clk(q->kind) * kClockGHz * 1e3;  // region bytes per us per SM
     int max_band = 0;
     for (int i = 0; i < q->nbands; ++i) max_band = std::max(max_band, q->bands[i]);
-    int kmax = std::min({loops, (kWarps * max_band - 1) / 2, (kRegionBytes / 2 - 64) / q->C});
+    int kmax = std::min({loops, (kWarps * max_band - 1) / 2, (kRegionBytes / 2 - 64) / q->C});   // (upper bound)
     if (q->min_nbr_rows > 0) kmax = (int)std::min<int64_t>(kmax, q->min_nbr_rows);
     if (q->min_nbr_cols > 0) kmax = (int)std::min<int64_t>(kmax, q->min_nbr_cols);
     kmax = std::max(kmax, 1);
     const int k_lo = q->force_k > 0 ? q->force_k : 1, k_hi = q->force_k > 0 ? q->force_k : kmax;
     const bool dual = q->resident && q->dual;
+    const int warps = (dual && q->dual == 2) ? kWarps - 1 : kWarps;   // protocol-warp variant: 15 compute warps
     const double t_x = dual ? (q->peers ? kExchangeUsDualPeer : kExchangeUsDual)
                             : (q->peers ? kExchangeUsPeer : kExchangeUs);
     bool found = false;
@@ -58,7 +59,7 @@ extern "C" int pconv_plan(const pconv_plan_request_t* q, pconv_plan_t* out) {
         for (int bi = 0; bi < q->nbands; ++bi) {
             const int R = q->bands[bi];
             if (q->force_R > 0 && R != q->force_R) continue;
-            const int RH = kWarps * R, th_max = RH - 2 * k;
+            const int RH = warps * R, th_max = RH - 2 * k;
             if (th_max < (q->resident ? k : 1)) continue;
             int64_t nty = ceil_div(q->tile_rows, th_max);
             if (dual) nty += nty & 1;                       // two virtual tile rows per CTA

@@ -154,6 +154,16 @@ def resident2_band_heights(kind: int) -> list[int]:
     return [int(buf[i]) for i in range(n)]
 
 
+def resident3_band_heights(kind: int) -> list[int]:
+    """Band heights compiled for the split-phase resident kernel with a protocol warp (experimental)."""
+    L = lib()
+    if not hasattr(L, "pconv_resident3_band_heights"):
+        return []
+    buf = (C.c_int * 16)()
+    n = int(L.pconv_resident3_band_heights(kind, buf, 16))
+    return [int(buf[i]) for i in range(n)]
+
+
 def malloc(nbytes: int) -> int:
     p = C.c_void_p()
     _check(lib().pconv_cuda_malloc(C.byref(p), nbytes), "cudaMalloc")
@@ -283,7 +293,8 @@ def unpack_rect(tile: int, pitch: int, row0: int, byte0: int, rows: int, nbytes:
 
 
 def kernel_prepare(kind: int, channels: int, band: int, resident: bool | int = False) -> None:
-    """``resident``: False/0 stream kernel, True/1 resident kernel, 2 split-phase resident kernel."""
+    """``resident``: False/0 stream kernel, True/1 resident kernel, 2 split-phase resident kernel,
+    3 split-phase + protocol warp."""
     _check(lib().pconv_kernel_prepare(kind, channels, band, int(resident)), "kernel_prepare")
 
 

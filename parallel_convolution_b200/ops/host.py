@@ -116,7 +116,7 @@ def split(extent: int, parts: int, idx: int) -> tuple[int, int]:
 def plan(tile_rows: int, tile_cb: int, Cn: int, kind: int, loops: int, bands: list[int], *,
          min_nbr_rows: int = 0, min_nbr_cols: int = 0, sms: int = 148, force_k: int = 0,
          force_R: int = 0, resident: bool = False, peers: bool = False,
-         dual: bool = False) -> PlanResult | None:
+         dual: bool | int = False) -> PlanResult | None:
     """Native launch planner (csrc/host/planner.cpp). None when no plan is feasible."""
     q = PlanRequest()
     q.tile_rows, q.tile_cb, q.min_nbr_rows, q.min_nbr_cols = tile_rows, tile_cb, min_nbr_rows, min_nbr_cols

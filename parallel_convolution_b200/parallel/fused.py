@@ -224,7 +224,7 @@ class TileDriver:
 
 def make_resident_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int | None = None,
                        sms: int | None = None, bands: list[int] | None = None,
-                       band: int | None = None, peers: bool = False, dual: bool = False) -> StreamPlan | None:
+                       band: int | None = None, peers: bool = False, dual: bool | int = False) -> StreamPlan | None:
     """Plan for the persistent resident kernel (``dual``: its split-phase variant), or None when the
     tile does not fit on chip."""
     from .plan import plan_resident

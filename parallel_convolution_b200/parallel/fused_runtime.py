@@ -43,6 +43,7 @@ class FusedRuntime:
         self.sms = K.sm_count()
         self.bands = K.band_heights(filt.kind)
         self.bands2 = K.resident2_band_heights(filt.kind)    # split-phase resident kernel
+        self.bands3 = K.resident3_band_heights(filt.kind)    # ... with a protocol warp (experimental)
         rows = grid.max_tile_rows()
         self.peers = None
         if world > 1:
@@ -68,6 +69,7 @@ class FusedRuntime:
         self._plans: dict[int, StreamPlan] = {}
         self._rplans: dict[int, StreamPlan | None] = {}
         self._r2plans: dict[int, StreamPlan | None] = {}
+        self._r3plans: dict[int, StreamPlan | None] = {}
         # virtual ranks in resident mode need their persistent kernels co-resident: one stream each,
         # and no two of them on one hardware queue (ops.cuda.MAX_CONNECTIONS) — beyond that, stream mode
         self._rank_streams = ({r: K.stream_create() for r in self.local_ranks}
@@ -141,14 +143,16 @@ class FusedRuntime:
         self._first_wait = self.epoch
         return len(self.drivers)
 
-    def resident_plan(self, loops: int, dual: bool = False) -> StreamPlan | None:
-        """Plan of the persistent kernel (``dual``: its split-phase variant); None if it cannot hold the tile."""
-        cache = self._r2plans if dual else self._rplans
+    def resident_plan(self, loops: int, dual: bool | int = False) -> StreamPlan | None:
+        """Plan of the persistent kernel (``dual``: 1/True its split-phase variant, 2 the split-phase
+        variant with a protocol warp); None if it cannot hold the tile."""
+        dual = int(dual)
+        cache = (self._rplans, self._r2plans, self._r3plans)[dual]
         if len(self.local_ranks) > 1 and not self._rank_streams:
             return None        # too many virtual ranks for concurrent persistent kernels
         if loops not in cache:
             nloc = len(self.local_ranks)
-            bands = self.bands2 if dual else self.bands
+            bands = (self.bands, self.bands2, self.bands3)[dual]
             if dual and (not bands or (self.band and self.band not in bands)):
                 cache[loops] = None
             else:
@@ -157,11 +161,14 @@ class FusedRuntime:
                     peers=self.world > 1, dual=dual)
         return cache[loops]
 
+    _VARIANT = {"stream": -1, "resident": 0, "resident2": 1, "resident3": 2}
+
     def _plan_cache(self, mode: str) -> dict:
-        return {"stream": self._plans, "resident": self._rplans, "resident2": self._r2plans}[mode]
+        return {"stream": self._plans, "resident": self._rplans, "resident2": self._r2plans,
+                "resident3": self._r3plans}[mode]
 
     def plan_for(self, mode: str, loops: int) -> StreamPlan | None:
-        return self.plan(loops) if mode == "stream" else self.resident_plan(loops, mode == "resident2")
+        return self.plan(loops) if mode == "stream" else self.resident_plan(loops, self._VARIANT[mode])
 
     # -- on-device autotuning ----------------------------------------------------------------------
     def autotune(self, loops: int, max_candidates: int = 14, reps: int = 2) -> dict:
@@ -180,10 +187,10 @@ class FusedRuntime:
                 if mode == "stream":
                     p = make_plan(self.grid, self.filt, loops, k, self.sms, self.bands, R)
                 else:
-                    dual = mode == "resident2"
+                    var = self._VARIANT[mode]
                     p = make_resident_plan(self.grid, self.filt, loops, k, self.sms // len(self.local_ranks),
-                                           self.bands2 if dual else self.bands, R, peers=self.world > 1,
-                                           dual=dual)
+                                           (self.bands, self.bands2, self.bands3)[var], R,
+                                           peers=self.world > 1, dual=max(var, 0))
             except ValueError:
                 return
             if p is not None and (mode, p) not in cands:
@@ -192,6 +199,8 @@ class FusedRuntime:
         modes = [m for m in ("stream", "resident") if self.mode in ("auto", m)]
         if self.bands2 and (self.mode == "resident2" or (self.mode == "auto" and AUTO_RESIDENT2)):
             modes.append("resident2")
+        if self.bands3 and self.mode == "resident3":      # never picked automatically (not run on hardware yet)
+            modes.append("resident3")
         per_mode = max(4, max_candidates // max(1, len(modes)))
         for mode in modes:
             base = self.plan_for(mode, loops)
@@ -199,7 +208,7 @@ class FusedRuntime:
                 continue
             mine = len(cands)
             cands.append((mode, base))
-            bands = self.bands2 if mode == "resident2" else self.bands
+            bands = {"resident2": self.bands2, "resident3": self.bands3}.get(mode, self.bands)
             for k in sorted({max(1, base.k - 2), max(1, base.k - 1), base.k + 1, base.k + 2, base.k + 5,
                              max(1, base.k // 2), base.k * 2} - {base.k}):
                 if self.halo_depth or k > loops:
@@ -213,7 +222,7 @@ class FusedRuntime:
             own = sorted(cands[mine:], key=lambda mp: mp[1].est_us_per_launch *
                          (-(-loops // mp[1].k) if mp[0] == "stream" else 1))
             cands[mine:] = own[:per_mode]
-        saved = (self.mode, dict(self._plans), dict(self._rplans), dict(self._r2plans))
+        saved = (self.mode, dict(self._plans), dict(self._rplans), dict(self._r2plans), dict(self._r3plans))
         results = []
         for mode, p in cands:
             self.mode = mode
@@ -248,7 +257,7 @@ class FusedRuntime:
                 best = float(t.item())
             if best is not None:
                 results.append((best, mode, p))
-        self.mode, self._plans, self._rplans, self._r2plans = saved
+        self.mode, self._plans, self._rplans, self._r2plans, self._r3plans = saved
         if not results:
             return {}
         results.sort(key=lambda r: r[0])
@@ -263,7 +272,7 @@ class FusedRuntime:
         tuned = getattr(self, "_tuned", {}).get(loops)
         if tuned and self.mode == "auto":
             return tuned
-        if self.mode in ("stream", "resident", "resident2"):
+        if self.mode in ("stream", "resident", "resident2", "resident3"):
             if self.mode != "stream" and self.plan_for(self.mode, loops) is None:
                 raise ValueError(f"{self.mode} mode requested but the tile does not fit on chip")
             return self.mode
@@ -275,8 +284,8 @@ class FusedRuntime:
             return "resident"
         return "stream"
 
-    def _enqueue_resident(self, loops: int, dual: bool = False) -> tuple[StreamPlan, int]:
-        plan = self.resident_plan(loops, dual)
+    def _enqueue_resident(self, loops: int, variant: int = 0) -> tuple[StreamPlan, int]:
+        plan = self.resident_plan(loops, variant)
         nblocks = -(-loops // plan.k)
         first_wait, self._first_wait = getattr(self, "_first_wait", 0), 0
         signal = self.epoch + 1 if self.multi else 0
@@ -284,6 +293,8 @@ class FusedRuntime:
         params = {r: self.drivers[r].resident_params(plan, loops, self.parity, first_wait if self.multi else 0,
                                                      signal, self.cta_epoch, slot=self.slot,
                                                      wait_bank1=bank1) for r in self.local_ranks}
+        for p in params.values():
+            p.dual = variant            # 0 single-phase, 1 split-phase, 2 split-phase + protocol warp
         if self._rank_streams:
             fork = K.Event().record(self.stream)
             joins = []
@@ -308,7 +319,7 @@ class FusedRuntime:
             return None, 0
         mode = self.choose_mode(loops)
         if mode != "stream":
-            return self._enqueue_resident(loops, mode == "resident2")
+            return self._enqueue_resident(loops, self._VARIANT[mode])
         plan = self.plan(loops)
         ks = plan.launches(loops)
         n = len(self.local_ranks)
@@ -391,7 +402,7 @@ class FusedRuntime:
             return
         mode = self.choose_mode(loops)
         plan = self.plan_for(mode, loops)
-        resident = {"stream": 0, "resident": 1, "resident2": 2}[mode]
+        resident = self._VARIANT[mode] + 1
         key = (plan.R, resident)
         if key not in getattr(self, "_prepared", set()):
             K.kernel_prepare(self.filt.kind, self.grid.channels, plan.R, resident)

@@ -68,10 +68,11 @@ def plan_resident(tile_rows: int, tile_cb: int, C: int, kind: int, loops: int, *
                   min_nbr_rows: int | None = None, min_nbr_cols: int | None = None,
                   sms: int = DEFAULT_SMS, bands: list[int] | None = None, peers: bool = False,
                   force_k: int | None = None, force_R: int | None = None,
-                  dual: bool = False) -> StreamPlan | None:
-    """``dual``: plan the split-phase kernel (``bands`` are then its per-virtual-tile heights)."""
+                  dual: bool | int = False) -> StreamPlan | None:
+    """``dual``: 1/True plans the split-phase kernel (``bands`` are then its per-virtual-tile heights),
+    2 its protocol-warp variant (regions of 15*R rows)."""
     default = DEFAULT_DUAL_BANDS if dual else DEFAULT_BANDS
     return _to_plan(H.plan(tile_rows, tile_cb, C, kind, loops, sorted(bands or default[kind]),
                            min_nbr_rows=min_nbr_rows or 0, min_nbr_cols=min_nbr_cols or 0, sms=sms,
                            force_k=force_k or 0, force_R=force_R or 0, resident=True, peers=peers,
-                           dual=dual), dual)
+                           dual=int(dual)), bool(dual))
