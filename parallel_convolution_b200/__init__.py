@@ -12,10 +12,17 @@ Public API::
     out = eng.run(image_uint8, loops=100)
 """
 import os as _os
+import sys as _sys
 
-# Must be in the environment before ANY library creates the CUDA context (see ops/cuda.py): persistent
-# kernels of several virtual ranks need one hardware queue each.
-_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# Persistent kernels of several *virtual ranks* (N tiles on one GPU: tests, ConvEngine(workers=N)) need one
+# hardware queue each; CUDA reads CUDA_DEVICE_MAX_CONNECTIONS when the context is created. Ask for 32 only
+# if nobody chose a value and no CUDA context can exist yet; otherwise leave the environment alone —
+# ops.cuda.usable_connections() reads what is really in effect and the runtime falls back to the streaming
+# kernel when there are more virtual ranks than queues (never a silent deadlock).
+_torch = _sys.modules.get("torch")
+if "CUDA_DEVICE_MAX_CONNECTIONS" not in _os.environ and not (
+        _torch is not None and getattr(_torch, "cuda", None) is not None and _torch.cuda.is_initialized()):
+    _os.environ["CUDA_DEVICE_MAX_CONNECTIONS"] = "32"
 
 from .models.filters import Filter, available as available_filters  # noqa: E402,F401
 

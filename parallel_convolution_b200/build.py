@@ -37,13 +37,12 @@ def _pick_cxx() -> str:
 CXX = _pick_cxx()
 
 HOST_SOURCES = ["host/filters.cpp", "host/decomp.cpp", "host/cpu_engine.cpp", "host/rawio.cpp",
-                "host/planner.cpp"]
+                "host/planner.cpp", "host/xplan_emu.cpp"]
 HOST_ORACLE = "host/oracle.cpp"  # compiled separately at -O1 with contraction off
-CUDA_SOURCES = ["cuda/runtime.cu", "cuda/pack_kernels.cu", "cuda/stream_kernel.cu", "cuda/resident_kernel.cu",
+CUDA_SOURCES = ["cuda/runtime.cu", "cuda/pack_kernels.cu", "cuda/stream_kernel.cu", "cuda/persist_kernel.cu",
                 "cuda/stream_kind_sep.cu", "cuda/stream_kind_int.cu", "cuda/stream_kind_f32.cu",
-                "cuda/resident_kind_sep.cu", "cuda/resident_kind_int.cu", "cuda/resident_kind_f32.cu",
-                "cuda/resident2_kind_sep.cu", "cuda/resident2_kind_int.cu", "cuda/resident2_kind_f32.cu",
-                "cuda/resident3_kind_sep.cu", "cuda/resident3_kind_int.cu", "cuda/resident3_kind_f32.cu"]
+                "cuda/persist_sep_w8.cu", "cuda/persist_sep_w16.cu", "cuda/persist_int_w8.cu",
+                "cuda/persist_int_w16.cu", "cuda/persist_f32_w8.cu", "cuda/persist_f32_w16.cu"]
 
 CXXFLAGS = ["-std=c++17", "-fPIC", "-O3", "-ffp-contract=off", "-fopenmp", "-Wall",
             "-Wno-unknown-pragmas"]

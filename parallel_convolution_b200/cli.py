@@ -41,10 +41,14 @@ def build_parser() -> argparse.ArgumentParser:
                    help="builtin name (box, gaussian, edge, sharpen, laplacian, emboss, sobel_x, sobel_y, "
                         "identity), 'a,b,c,d,e,f,g,h,i[/div]', nine floats, or a file")
     p.add_argument("--backend", default="auto", choices=["auto", "fused", "nccl", "cpu", "host"])
-    p.add_argument("--mode", default="auto", choices=["auto", "stream", "resident", "resident2", "resident3"],
-                   help="fused backend: streaming launches, the persistent on-chip kernel, or its "
-                        "split-phase variant (exchange overlapped with arithmetic); resident3 = split-phase "
-                        "with a protocol warp (experimental)")
+    p.add_argument("--mode", default="auto", choices=["auto", "stream", "resident"],
+                   help="fused backend kernel: resident = ONE persistent launch per run, the tile stays in "
+                        "registers and CTAs push their halos into each other's inboxes (needs the tile to "
+                        "fit on chip); stream = k fused iterations per launch, any image size; auto = "
+                        "resident when it fits")
+    p.add_argument("--warps", type=int, default=0, choices=[0, 8, 16],
+                   help="persistent kernel: warps per CTA (8 = two CTAs per SM hide each other's exchanges, "
+                        "16 = one CTA per SM; 0 = planner / autotuner decides)")
     p.add_argument("--gpus", "--workers", dest="workers", type=int, default=None,
                    help="single process: decompose over N virtual ranks on one GPU")
     p.add_argument("-np", "--np", dest="nprocs", type=int, default=None, metavar="N",
@@ -153,7 +157,7 @@ def main(argv: list[str] | None = None) -> int:
         with nvtx_range("pconv:setup"):
             eng = ConvEngine(width=a.width, height=a.height, channels=channels, filter=a.filter,
                              backend=a.backend, workers=a.workers, grid=grid, halo_depth=a.halo_depth,
-                             mode=a.mode, threads=a.threads, timeout_ms=a.timeout_ms,
+                             mode=a.mode, warps=a.warps or None, threads=a.threads, timeout_ms=a.timeout_ms,
                              slots=3 if a.batch else 1)
         if a.inject_drop_signal is not None and hasattr(eng._impl, "drivers"):
             for r, d in eng._impl.drivers.items():

@@ -35,8 +35,8 @@ typedef struct pconv_sync {
     uint32_t signal_value;      // last CTA stores this to every remote flag (0: no signal)
     uint64_t timeout_ns;        // watchdog for the spin (0: default 10 s)
     uint64_t* status;           // [0] error code (1 = watchdog fired), [1] max wait ns, [2] sum wait
-                                // ns, [3] number of waits; resident kernel probe CTA: [4] publish ns,
-                                // [5] flag+wait ns, [6] halo reload ns, [7] compute ns, [8] exchanges
+                                // ns, [3] number of waits; persistent kernel probe CTA: [4] push ns,
+                                // [5] signal+wait ns, [6] inbox->register ns, [7] compute ns, [8] exchanges
     int32_t inject_delay_ns;    // fault injection: delay my signal by this much (tests)
     int32_t inject_drop_signal; // fault injection: never signal (the peer's watchdog must fire)
 } pconv_sync_t;
@@ -74,42 +74,43 @@ int pconv_stream_run(const pconv_stream_params_t* pp, int nranks, const int32_t*
 // so that back-to-back steps need no host barrier (bench.py, streaming ingest).
 int pconv_sync_launch(const pconv_sync_t* s, void* stream);
 // Force the lazy module load of the kernel a plan will use (cudaFuncGetAttributes), so that the
-// first timed run does not pay ~10 ms of one-time SASS loading. resident: 0 stream kernel,
-// 1 resident kernel, 2 split-phase resident kernel, 3 split-phase + protocol warp (experimental).
-int pconv_kernel_prepare(int kind, int C, int R, int resident);
+// first timed run does not pay ~10 ms of one-time SASS loading (stream kernel; the persistent kernel
+// is loaded by pconv_persist_capacity).
+int pconv_kernel_prepare(int kind, int C, int R);
 // Band heights compiled for a filter kind; returns the count, fills out[0..cap).
 int pconv_stream_band_heights(int kind, int* out, int cap);
 
-// ---- resident kernel: the whole tile stays in registers for ALL iterations of a run ------------
-// One persistent launch: CTA (ti,tj) keeps its region in registers, and every k iterations the CTAs
-// exchange k-deep border strips through the (L2-resident / peer-mapped) tile buffers with per-CTA
-// epoch flags — between CTAs of one GPU and, for border CTAs, straight across NVLink.
-// Requires nty*ntx <= #SMs (all CTAs co-resident; launched cooperatively) and identical tile
-// shapes on every rank.
-typedef struct pconv_resident_params {
+// ---- persistent kernel: the whole tile stays in registers for ALL iterations of a run ---------
+// One cooperative launch: CTA (ti,tj) keeps its region (W*R rows x 512 B) in registers; every k
+// iterations the CTAs PUSH k-deep border blocks into each other's inbox slots (an exchange arena per
+// rank, peer-mapped across GPUs), signal with one release-store per neighbour and fetch their own inbox
+// with bulk async copies on an mbarrier (persist_kernel.cuh, common/xplan.h). W = 8 runs two CTAs per
+// SM (one CTA's exchange hides behind the other's arithmetic), W = 16 one.
+// Requires identical tile shapes on every rank and all nty*ntx CTAs co-resident.
+typedef struct pconv_persist_params {
     pconv_geometry_t g;
-    const uint8_t* src_a[9]; // parity-0 buffers by direction: the input image, then even exchanges
-    const uint8_t* src_b[9]; // parity-1 buffers by direction: odd exchanges
-    uint8_t* self_a;         // == src_a[4], writable
-    uint8_t* self_b;         // == src_b[4], writable
+    const uint8_t* src[9];   // input tiles by direction (NULL: no such neighbour); [4] is mine
+    uint8_t* dst;            // my output tile (the other buffer of the ping-pong pair)
     pconv_filter_t filt;
     int32_t loops;           // total iterations in this launch (>= 1)
     int32_t k;               // iterations between exchanges
-    int32_t TH, TWB, HB;     // region interior / halo geometry (as in the stream kernel)
-    int32_t R;               // band height
+    int32_t TH, TWB, HB;     // region interior / halo geometry (TWB + 2*HB == 512)
+    int32_t R, W;            // band height, warps per CTA (8 or 16)
     int32_t nty, ntx;        // CTA grid (same on every rank)
-    uint32_t* cta_flags;     // [(nty+2)*(ntx+2)] epochs, incl. a ring mirrored from neighbour GPUs
-    uint32_t* remote_cta_flags[9];  // the same array on neighbour d (peer-mapped) or NULL
-    uint32_t epoch_base;     // exchange b (1-based) uses epoch_base + b; host advances it per run
-    uint32_t dual;           // 1: split-phase kernel (two virtual tile rows per CTA, nty counts them; even);
-                             // 2: the same with a protocol warp (resident3_kernel.cuh, experimental)
+    uint8_t* arena[9];       // exchange arenas by rank direction: [4] mine, others peer-mapped or NULL
+    int64_t arena_bytes;     // size of every arena
+    uint32_t epoch_base;     // exchange b (1-based) carries epoch_base + b; the host advances it by
+                             // ceil(loops/k) - 1 per run (epochs stay contiguous: the inbox parity alternates)
+    uint32_t peer_scope;     // 1: neighbouring ranks are other GPUs (system-scope flags)
     pconv_sync_t sync;       // launch-level protocol, identical to the stream kernel's
-} pconv_resident_params_t;
-// The result lands in parity (ceil(loops/k) & 1): 1 -> self_b, 0 -> self_a.
-int pconv_resident_launch(const pconv_resident_params_t* p, void* stream);
-// Band heights (rows per warp per virtual tile) compiled for the split-phase kernel.
-int pconv_resident2_band_heights(int kind, int* out, int cap);
-int pconv_resident3_band_heights(int kind, int* out, int cap);
+} pconv_persist_params_t;
+int pconv_persist_launch(const pconv_persist_params_t* p, void* stream);
+// Bytes of exchange arena this plan needs (flags + two inbox parities for every CTA); <0: bad plan.
+int64_t pconv_persist_arena_bytes(const pconv_persist_params_t* p);
+// CTAs of the plan's kernel instance the device keeps resident (also loads the module); <0: error.
+int pconv_persist_capacity(const pconv_persist_params_t* p);
+// Band heights compiled for a filter kind (same list for W = 8 and W = 16).
+int pconv_persist_band_heights(int kind, int* out, int cap);
 
 // ---- runtime -----------------------------------------------------------------------------------
 int pconv_cuda_device_count(void);

@@ -1,0 +1,339 @@
+// Persistent kernel with an asynchronous, pushed halo exchange (the default multi-iteration path).
+//
+// One cooperative launch per run. The rank's tile is spread over nty x ntx CTAs; each CTA keeps its
+// region (W*R rows x 512 B, stencil_core.cuh) in REGISTERS for all iterations. CTAs are W = 8 warps
+// (two co-resident per SM) or W = 16 (one per SM): with two CTAs per SM the warp schedulers overlap
+// one CTA's exchange latency with the other CTA's arithmetic — the reference's schedule
+// "post sends/receives -> interior -> wait -> border" (mpi/mpi_conv.c:164-248) with the SM itself as
+// the overlap engine.
+//
+// Exchange b (every k iterations), see common/xplan.h for the geometry:
+//   1. PUSH   every thread stores the chunks of its band that lie in the k-deep border of the CTA's
+//             interior straight from registers into the inbox slot (parity b&1) of each neighbouring CTA
+//             that needs them — plain 128-bit stores; the slot lives on the CONSUMER's GPU, so across
+//             GPUs these are fire-and-forget NVLink writes through the peer-mapped arena.
+//   2. SIGNAL __syncthreads; lanes 0..8 of warp 0 release-store the epoch into "their" neighbour's flag
+//             word (st.release.gpu, or .sys when the neighbour is another GPU).
+//   3. FETCH  lane 0 arms the CTA's mbarrier with the expected byte count; lanes 0..8 each poll ONE
+//             local flag word (the one their source neighbour writes) and, as soon as it shows the epoch,
+//             issue ONE bulk async copy (cp.async.bulk global -> shared, complete_tx on the mbarrier)
+//             of that neighbour's block into the shared-memory inbox.
+//   4. WAIT   all threads wait on the mbarrier (hardware sleep, no spinning on memory), then read their
+//             halo chunks from the shared-memory inbox with 128-bit loads and iterate k more times.
+// No thread of a consumer ever reads remote memory, nothing is staged or packed, and there is no
+// CTA-wide barrier between "flags seen" and "halo in registers". Two inbox parities make the blocks
+// double-buffered: a producer can only overwrite parity p (epoch e+2) after it received the consumer's
+// epoch e+1, which the consumer sends after it finished reading epoch e.
+//
+// The tile buffers in global memory are touched twice per run: the initial region load (through the
+// 3x3 owner lookup of region_io.cuh, halo from the neighbours' input tiles) and the final interior
+// store. Launch-level flags (pconv_sync_t) order those against the neighbouring ranks exactly as in the
+// streaming kernel.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "../common/xplan.h"
+#include "pconv_cuda.h"
+#include "region_io.cuh"
+#include "runtime_internal.h"
+#include "stencil_core.cuh"
+
+namespace pconv {
+
+struct PersistArgs {
+    pconv_geometry_t g;
+    SourceSet src;          // input tiles by direction (initial load only)
+    uint8_t* dst;           // my output tile
+    FilterDev f;
+    XGeom x;
+    uint8_t* arena[9];      // exchange arenas by RANK direction ([4] mine, peers: mapped; NULL: absent)
+    int loops;
+    uint32_t epoch_base;    // exchange b (1-based) carries epoch epoch_base + b
+    uint32_t peer_scope;    // 1: neighbouring ranks are other GPUs (system-scope release / acquire)
+    pconv_sync_t sync;
+};
+
+// ---- mbarrier / bulk-copy primitives (PTX ISA 8.0+, sm_90+; SASS: SYNCS.*, UBLKCP) ---------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// global -> shared bulk copy (bytes: multiple of 16), completes `bytes` of transaction on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Per-CTA exchange tables (shared memory, filled once per launch).
+struct XTables {
+    uint8_t* dst_slot[2][9];     // where my block for destination D goes: base of the consumer's slot, by parity
+    uint32_t* dst_flag[9];       // the consumer's flag word I write
+    const uint8_t* my_slot[2];   // my own inbox slot in global memory, by parity
+    const uint32_t* my_flags;    // my 9 flag words (word s written by the neighbour in direction s)
+    uint32_t blk_bytes[9];       // bytes of the block received from direction s
+    uint32_t total_bytes;        // sum over existing sources
+    uint32_t nbr_mask;           // bit D: a CTA exists in direction D (sources == destinations)
+    uint32_t remote_mask;        // bit D: that CTA belongs to another rank
+};
+
+template <int W>
+struct PersistSmem {
+    EdgeBuffersT<W> eb;
+    XTables t;
+    alignas(8) uint64_t mbar;
+    unsigned long long wait_ns;
+    uint32_t dead;                 // a watchdog fired in this CTA: stop waiting, run through (status[0] is set)
+    alignas(128) uint4 inbox[1];   // slot_chunks entries (dynamic)
+};
+
+template <int KIND, int C, int R, int W>
+__global__ void __launch_bounds__(W * 32, 16 / W)
+persist_kernel(const __grid_constant__ PersistArgs A) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    PersistSmem<W>& S = *reinterpret_cast<PersistSmem<W>*>(smem_raw);
+    const pconv_geometry_t& g = A.g;
+    const XGeom& x = A.x;
+    constexpr int RH = W * R;
+    const int k = x.k, nh = x.nh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ti = blockIdx.x / x.ntx, tj = blockIdx.x % x.ntx;
+    const int vr = xp_vr(x, ti), vc = xp_vc(x, tj);
+    const int64_t gr0 = g.row_lo[1] + (int64_t)ti * x.TH - k;
+    const int64_t gb0 = g.cb_lo[1] + (int64_t)tj * x.TWB - x.HB;
+    const int rr0 = warp * R;
+    const int64_t grw = gr0 + rr0;
+    const int64_t gb = gb0 + 16 * lane;
+
+    // ---- one-time setup: exchange tables, mbarrier -------------------------------------------------
+    if (threadIdx.x < 9) {
+        const int D = (int)threadIdx.x;
+        bool exists = false, remote = false;
+        if (D != 4) {
+            const XPeer p = xp_peer(x, ti, tj, D);
+            uint8_t* arena = A.arena[p.rank_dir];
+            exists = arena != nullptr;
+            remote = p.rank_dir != 4;
+            S.t.dst_slot[0][D] = exists ? arena + xp_slot_byte(x, p.cta, 0) : nullptr;
+            S.t.dst_slot[1][D] = exists ? arena + xp_slot_byte(x, p.cta, 1) : nullptr;
+            // I am the consumer's neighbour in direction 8-D
+            S.t.dst_flag[D] = exists ? reinterpret_cast<uint32_t*>(arena) + xp_flag_word(p.cta, 8 - D) : nullptr;
+            const XBlock b = xp_block(x, D, vr, vc);
+            S.t.blk_bytes[D] = exists ? (uint32_t)(b.nrows * b.width * 16) : 0u;
+        } else {
+            S.t.blk_bytes[4] = 0u;
+            S.t.my_slot[0] = A.arena[4] + xp_slot_byte(x, (int)blockIdx.x, 0);
+            S.t.my_slot[1] = A.arena[4] + xp_slot_byte(x, (int)blockIdx.x, 1);
+            S.t.my_flags = reinterpret_cast<const uint32_t*>(A.arena[4]) + xp_flag_word((int)blockIdx.x, 0);
+            S.wait_ns = 0ull;
+            S.dead = 0u;
+            mbar_init(&S.mbar, 1u);
+            fence_mbar_init();
+        }
+        const unsigned em = __ballot_sync(0x1ffu, exists), rm = __ballot_sync(0x1ffu, exists && remote);
+        if (D == 0) { S.t.nbr_mask = em; S.t.remote_mask = rm; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int s = 0; s < 9; ++s) tot += S.t.blk_bytes[s];
+        S.t.total_bytes = tot;
+    }
+
+    // ---- launch-level protocol: the neighbours' input tiles are in place ---------------------------
+    if (A.sync.wait_value != 0u && threadIdx.x < 9 && threadIdx.x != 4) {
+        const int dy = (int)threadIdx.x / 3, dx = (int)threadIdx.x % 3;
+        const bool rows_hit = dy == 0 ? gr0 < g.row_lo[1] : dy == 2 ? gr0 + RH > g.row_lo[2] : true;
+        const bool cols_hit = dx == 0 ? gb0 < g.cb_lo[1] : dx == 2 ? gb0 + kSP > g.cb_lo[2] : true;
+        if (rows_hit && cols_hit && A.src.p[threadIdx.x] != nullptr) {
+            const uint64_t ns = wait_flag(A.sync.local_flags + threadIdx.x, A.sync.wait_value,
+                                          A.sync.timeout_ns, A.sync.status);
+            atomicMax(&S.wait_ns, (unsigned long long)ns);
+        }
+    }
+    __syncthreads();
+
+    // ---- load the region once ---------------------------------------------------------------------
+    uint4 rows[R];
+    load_band<R>(rows, g, A.src, grw, gb);
+    bool need_cols;
+    const uint4 cmask = column_mask(g, gb0, &need_cols);
+    uint32_t rowmask = 0;
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+        if (grw + i >= 0 && grw + i < g.img_rows) rowmask |= 1u << i;
+    const bool masked = need_cols || gr0 < 0 || gr0 + RH > g.img_rows;
+
+    // Row / lane classes of this thread's band (common/xplan.h), fixed for the whole run.
+    const XThread xt = xp_thread(x, vr, vc, rr0, lane, R);
+    const uint32_t nbr_mask = S.t.nbr_mask, remote_mask = S.t.remote_mask;
+
+    const bool probe = A.sync.status != nullptr && threadIdx.x == 0 &&
+                       blockIdx.x == (unsigned)((x.nty / 2) * x.ntx + x.ntx / 2);
+    uint64_t t_pub = 0, t_wait = 0, t_load = 0, t_comp = 0, t_mark = probe ? globaltimer_ns() : 0;
+    auto lap = [&](uint64_t& acc) {
+        if (probe) { const uint64_t t = globaltimer_ns(); acc += t - t_mark; t_mark = t; }
+    };
+
+    const int nblocks = (A.loops + k - 1) / k;
+    uint32_t phase = 0;
+    for (int b = 0; b < nblocks; ++b) {
+        if (b > 0) {
+            const uint32_t epoch = A.epoch_base + (uint32_t)b;
+            const int par = (int)(epoch & 1u);
+            // ---- 1. push my border chunks into the neighbours' inboxes ------------------------------
+#pragma unroll
+            for (int D = 0; D < 9; ++D) {
+                if (D == 4 || !((nbr_mask >> D) & 1u)) continue;
+                uint32_t m;
+                int idx0, stride;
+                if (xp_push(x, xt, D, vr, vc, rr0, lane, &m, &idx0, &stride)) {
+                    uint4* base = reinterpret_cast<uint4*>(S.t.dst_slot[par][D]) + idx0;
+#pragma unroll
+                    for (int i = 0; i < R; ++i)
+                        if ((m >> i) & 1u) __stcg(base + i * stride, rows[i]);
+                }
+            }
+            __syncthreads();
+            lap(t_pub);
+            // ---- 2./3. signal the consumers, arm my inbox, fetch each block as its flag arrives -------
+            if (warp == 0) {
+                const bool mine = lane < 9 && ((nbr_mask >> lane) & 1u);
+                const bool far = A.peer_scope && ((remote_mask >> lane) & 1u);
+                // (the release store alone publishes the pushed chunks: the CTA's stores happen-before
+                //  it through the barrier above — causality order is cumulative)
+                if (mine) {
+                    if (far) st_release_sys(S.t.dst_flag[lane], epoch);
+                    else st_release_gpu(S.t.dst_flag[lane], epoch);
+                }
+                if (lane == 0) mbar_arrive_expect_tx(&S.mbar, S.t.total_bytes);
+                __syncwarp();
+                if (mine) {
+                    const uint32_t* fl = S.t.my_flags + lane;
+                    uint64_t ns = 0;
+                    if (!*(volatile uint32_t*)&S.dead)
+                        ns = far ? wait_flag<true>(fl, epoch, A.sync.timeout_ns, A.sync.status)
+                                 : wait_flag<false>(fl, epoch, A.sync.timeout_ns, A.sync.status);
+                    if (ns) atomicMax(&S.wait_ns, (unsigned long long)ns);
+                    if (ns > A.sync.timeout_ns) *(volatile uint32_t*)&S.dead = 1u;   // never hang the box
+                    fence_proxy_async();   // the block was written through the generic proxy
+                    bulk_g2s(&S.inbox[x.off[lane]], S.t.my_slot[par] + (size_t)x.off[lane] * 16,
+                             S.t.blk_bytes[lane], &S.mbar);
+                }
+            }
+            // ---- 4. wait for the inbox, refresh my halo from shared memory ---------------------------
+            if (!mbar_try_wait(&S.mbar, phase)) {
+                const uint64_t t0 = globaltimer_ns();
+                while (!mbar_try_wait(&S.mbar, phase)) {
+                    if (globaltimer_ns() - t0 > 2 * A.sync.timeout_ns) {   // (the pollers time out first)
+                        if (A.sync.status) atomicExch(reinterpret_cast<unsigned long long*>(A.sync.status), 2ull);
+                        break;
+                    }
+                }
+            }
+            phase ^= 1u;
+            lap(t_wait);
+#pragma unroll
+            for (int grp = 0; grp < 3; ++grp) {
+                uint32_t m;
+                int src, idx0, stride;
+                if (xp_fetch(x, xt, grp, vr, vc, rr0, lane, &src, &m, &idx0, &stride) && ((nbr_mask >> src) & 1u)) {
+                    const uint4* p = &S.inbox[idx0];
+#pragma unroll
+                    for (int i = 0; i < R; ++i)
+                        if ((m >> i) & 1u) rows[i] = p[i * stride];
+                }
+            }
+            lap(t_load);
+        }
+        // ---- 5. iterate ---------------------------------------------------------------------------
+        const int kb = min(k, A.loops - b * k);
+        if (masked) region_iterate<KIND, C, R, true, W>(rows, S.eb, kb, cmask, rowmask, need_cols, A.f);
+        else region_iterate<KIND, C, R, false, W>(rows, S.eb, kb, cmask, rowmask, need_cols, A.f);
+        __syncthreads();  // edge buffers: the next block restarts at parity 0; inbox reads are done
+        lap(t_comp);
+    }
+    if (probe) {
+        unsigned long long* st = reinterpret_cast<unsigned long long*>(A.sync.status);
+        atomicAdd(st + 4, (unsigned long long)t_pub);
+        atomicAdd(st + 5, (unsigned long long)t_wait);
+        atomicAdd(st + 6, (unsigned long long)t_load);
+        atomicAdd(st + 7, (unsigned long long)t_comp);
+        atomicAdd(st + 8, (unsigned long long)(nblocks - 1));
+    }
+
+    // ---- final interior -> my output tile -----------------------------------------------------------
+    store_band<R>(rows, xt.hcls == 1 ? xt.m_int : 0u, A.dst, g, grw, gb);
+    if (threadIdx.x == 0 && S.wait_ns) record_wait(A.sync.status, S.wait_ns);
+
+    // ---- launch-level protocol: publish "run done" -------------------------------------------------
+    if (A.sync.signal_value != 0u) {
+        __syncthreads();
+        if (threadIdx.x == 0) {   // acq_rel ticket: releases this CTA's stores, acquires the others'
+            const uint32_t ticket = atom_add_acq_rel_gpu(A.sync.done_counter, 1u);
+            if (ticket == gridDim.x - 1) {
+                *A.sync.done_counter = 0u;
+                if (!A.sync.inject_drop_signal) {
+                    fence_acq_rel_sys();
+#pragma unroll
+                    for (int d = 0; d < 9; ++d)
+                        if (d != 4 && A.sync.remote_flags[d] != nullptr)
+                            st_release_sys(A.sync.remote_flags[d], A.sync.signal_value);
+                }
+            }
+        }
+    }
+}
+
+using PersistFn = void (*)(const PersistArgs);
+
+// Band heights compiled in, per warps-per-CTA. The Gaussian path (the reference's only filter and the
+// headline benchmark) gets a fine ladder so that a tile divides evenly over the SMs at every GPU count.
+#define PCONV_PER_R_SEP(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(10) X(12) X(14)
+#define PCONV_PER_R_INT(X) X(2) X(4) X(7) X(10)
+#define PCONV_PER_R_F32(X) X(2) X(4) X(6) X(8) X(10)
+
+template <int KIND, int C, int W>
+static PersistFn pick_persist_r(int R) {
+#define CASE(RR) if (R == RR) return persist_kernel<KIND, C, RR, W>;
+    if constexpr (KIND == PCONV_KIND_F32) { PCONV_PER_R_F32(CASE) }
+    else if constexpr (KIND == PCONV_KIND_INT) { PCONV_PER_R_INT(CASE) }
+    else { PCONV_PER_R_SEP(CASE) }
+#undef CASE
+    return nullptr;
+}
+
+template <int KIND, int W>
+static PersistFn pick_persist_c(int C, int R) {
+    switch (C) {
+        case 1: return pick_persist_r<KIND, 1, W>(R);
+        case 3: return pick_persist_r<KIND, 3, W>(R);
+        case 4: return pick_persist_r<KIND, 4, W>(R);
+        default: return nullptr;
+    }
+}
+
+// one definition per translation unit persist_{sep,int,f32}_w{8,16}.cu
+PersistFn pick_persist_sep_w8(int C, int R);
+PersistFn pick_persist_sep_w16(int C, int R);
+PersistFn pick_persist_int_w8(int C, int R);
+PersistFn pick_persist_int_w16(int C, int R);
+PersistFn pick_persist_f32_w8(int C, int R);
+PersistFn pick_persist_f32_w16(int C, int R);
+
+}  // namespace pconv

@@ -1,0 +1,6 @@
+// Instantiates persist_kernel<PCONV_KIND_SEP121, C, R, 8> for every compiled channel stride and band height.
+#include "persist_kernel.cuh"
+
+namespace pconv {
+PersistFn pick_persist_sep_w8(int C, int R) { return pick_persist_c<PCONV_KIND_SEP121, 8>(C, R); }
+}  // namespace pconv

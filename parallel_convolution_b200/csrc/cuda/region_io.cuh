@@ -35,7 +35,7 @@ static __device__ __noinline__ uint4 load_chunk_bytes(const pconv_geometry_t& g,
     uint32_t w[4] = {0u, 0u, 0u, 0u};
     for (int t = 0; t < 16; ++t) {
         const int64_t b = gb + t;
-        if (b < 0 || b >= g.img_cb) continue;
+        if (b < g.cb_lo[0] || b >= g.cb_lo[3]) continue;   // outside the 3x3 tile window: zero
         const int oc = owner_of(b, g.cb_lo);
         const int d = orow * 3 + oc;
         const uint8_t* base = s.p[d];
@@ -52,10 +52,12 @@ static __device__ __noinline__ uint4 load_chunk_bytes(const pconv_geometry_t& g,
 __device__ __forceinline__ uint4 load_chunk(const pconv_geometry_t& g, const SourceSet& s,
                                             int64_t gr, int64_t gb) {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    if (gr < 0 || gr >= g.img_rows || gb + 16 <= 0 || gb >= g.img_cb) return z;
+    // (the window [row_lo[0], row_lo[3]) x [cb_lo[0], cb_lo[3]) never sticks out of the image; what lies
+    //  beyond it but inside the image belongs to a tile two steps away and is never needed: zero)
+    if (gr < g.row_lo[0] || gr >= g.row_lo[3] || gb + 16 <= g.cb_lo[0] || gb >= g.cb_lo[3]) return z;
     const int orow = owner_of(gr, g.row_lo);
     const int64_t lrow = gr - g.row_lo[orow];
-    if (gb >= 0 && gb + 16 <= g.img_cb) {
+    if (gb >= g.cb_lo[0] && gb + 16 <= g.cb_lo[3]) {
         const int oc = owner_of(gb, g.cb_lo);
         if (owner_of(gb + 15, g.cb_lo) == oc) {
             const int d = orow * 3 + oc;
@@ -81,14 +83,17 @@ __device__ __forceinline__ void load_band(uint4 (&rows)[R], const pconv_geometry
                                           const SourceSet& s, int64_t gr0, int64_t gb,
                                           uint32_t mask = 0xffffffffu) {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    const bool col_out = gb + 16 <= 0 || gb >= g.img_cb;
-    const bool col_whole = gb >= 0 && gb + 16 <= g.img_cb;
-    const int oc = owner_of(gb < 0 ? 0 : gb, g.cb_lo);
+    // Everything is clipped to the 3x3 tile window [row_lo[0], row_lo[3]) x [cb_lo[0], cb_lo[3]): a region
+    // overhang that reaches past the adjacent tile (small tiles, >= 3 tile rows/columns) is never needed
+    // and must not be read — it would fall outside that neighbour's buffer.
+    const bool col_out = gb + 16 <= g.cb_lo[0] || gb >= g.cb_lo[3];
+    const bool col_whole = gb >= g.cb_lo[0] && gb + 16 <= g.cb_lo[3];
+    const int oc = owner_of(gb < g.cb_lo[0] ? g.cb_lo[0] : gb, g.cb_lo);
     const bool one_owner = col_whole && owner_of(gb + 15, g.cb_lo) == oc;
     const int64_t cofs = gb - g.cb_lo[oc];
     // band-relative row boundaries, clamped to [0, R]
     auto rel = [&](int64_t v) { v -= gr0; return (int)(v < 0 ? 0 : (v > R ? R : v)); };
-    const int i_lo = rel(0), i_hi = rel(g.img_rows);            // rows inside the image
+    const int i_lo = rel(g.row_lo[0]), i_hi = rel(g.row_lo[3]);  // rows inside the tile window
     const int n1 = rel(g.row_lo[1]), n2 = rel(g.row_lo[2]);     // tile-row 0 below n1, 1 below n2, else 2
     // address of (image row gr0, my column) in the buffer of owning tile-row o, and whether 128-bit
     // loads are legal there

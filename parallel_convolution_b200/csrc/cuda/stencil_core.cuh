@@ -451,16 +451,18 @@ __device__ __forceinline__ void band_iterate(uint4 (&rows)[R], const uint4& top,
 }
 
 // Shared-memory exchange of band boundary rows between adjacent warps: edge[parity][warp][0|1][lane]
-struct EdgeBuffers {
-    uint4 row[2][kWarps][2][32];
+template <int W>
+struct EdgeBuffersT {
+    uint4 row[2][W][2][32];
 };
+using EdgeBuffers = EdgeBuffersT<kWarps>;
 
-// k fused iterations over a CTA region held in registers. One __syncthreads per iteration:
-// iteration `it` publishes into parity it&1 and everybody reads that parity after the barrier; the
-// next iteration publishes into the other parity, so a fast warp never overwrites rows a slow
-// warp is still reading.
-template <int KIND, int C, int R, bool MASKED>
-__device__ __forceinline__ void region_iterate(uint4 (&rows)[R], EdgeBuffers& eb, int k,
+// k fused iterations over a CTA region held in registers (W warps, R rows each). One __syncthreads
+// per iteration: iteration `it` publishes into parity it&1 and everybody reads that parity after the
+// barrier; the next iteration publishes into the other parity, so a fast warp never overwrites rows
+// a slow warp is still reading.
+template <int KIND, int C, int R, bool MASKED, int W = kWarps>
+__device__ __forceinline__ void region_iterate(uint4 (&rows)[R], EdgeBuffersT<W>& eb, int k,
                                                const uint4& cmask, uint32_t rowmask, bool need_cols,
                                                const FilterDev& f) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -471,7 +473,7 @@ __device__ __forceinline__ void region_iterate(uint4 (&rows)[R], EdgeBuffers& eb
         eb.row[par][warp][1][lane] = rows[R - 1];
         __syncthreads();
         const uint4 top = warp > 0 ? eb.row[par][warp - 1][1][lane] : zero;
-        const uint4 bottom = warp < kWarps - 1 ? eb.row[par][warp + 1][0][lane] : zero;
+        const uint4 bottom = warp < W - 1 ? eb.row[par][warp + 1][0][lane] : zero;
         band_iterate<KIND, C, R, MASKED>(rows, top, bottom, cmask, rowmask, need_cols, f);
     }
 }

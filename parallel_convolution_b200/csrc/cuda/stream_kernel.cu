@@ -159,10 +159,7 @@ extern "C" int pconv_sync_launch(const pconv_sync_t* s, void* stream) {
     return 0;
 }
 
-extern "C" int pconv_resident_prepare(int kind, int C, int R, int variant);   // resident_kernel.cu
-
-extern "C" int pconv_kernel_prepare(int kind, int C, int R, int resident) {
-    if (resident) return pconv_resident_prepare(kind, C, R, resident - 1);
+extern "C" int pconv_kernel_prepare(int kind, int C, int R) {
     KernelFn fn = pick_kernel(kind, C, R);
     if (!fn) return pconv_rt::fail("unsupported (filter kind, channels, band height) combination");
     cudaFuncAttributes at;

@@ -33,13 +33,12 @@ typedef struct pconv_plan_request {
     int64_t tile_rows, tile_cb;     // largest tile of the grid: rows, bytes per row
     int64_t min_nbr_rows, min_nbr_cols;  // smallest neighbouring tile extent in pixels (0: none)
     int32_t C, kind, loops, sms;
-    int32_t bands[8];               // band heights R compiled into the CUDA library
+    int32_t bands[16];              // band heights R compiled into the CUDA library
     int32_t nbands;
     int32_t force_k, force_R;       // 0: planner decides
-    int32_t resident;               // 1: plan the persistent resident kernel (all CTAs co-resident)
+    int32_t resident;               // 1: plan the persistent kernel (all CTAs co-resident)
     int32_t peers;                  // 1: neighbours sit on other GPUs (dearer exchanges)
-    int32_t dual;                   // resident only: 1 = split-phase kernel, two virtual tile rows per CTA;
-                                    // 2 = the same with a protocol warp (regions are 15*R rows)
+    int32_t warps;                  // persistent kernel: warps per CTA, 8 (two CTAs per SM) or 16
 } pconv_plan_request_t;
 typedef struct pconv_plan_result {
     int32_t k, R, TH, TWB, HB, ntx, nty, waves;
@@ -47,6 +46,13 @@ typedef struct pconv_plan_result {
 } pconv_plan_t;
 // 0: ok, 1: no feasible plan, <0: bad request.
 int pconv_plan(const pconv_plan_request_t* req, pconv_plan_t* out);
+
+// ---- CPU emulation of the persistent kernel's exchange protocol (csrc/host/xplan_emu.cpp) ----------
+// Replays every (rank, CTA, warp, lane) of a persist_kernel launch with the device code's own index
+// functions (common/xplan.h); out must equal the oracle. 0 ok, <0 rejected geometry / slot overflow.
+int pconv_xplan_emulate(const uint8_t* img, uint8_t* out, int64_t H, int64_t Wpx, int C,
+                        const pconv_filter_t* f, int loops, int gy, int gx, int k, int R, int W,
+                        int TH, uint32_t epoch_base);
 
 // ---- oracle: whole image, zero padded, scalar, deliberately naive ----------------------------
 // src/dst: H x (W*C) bytes, dense. Applies the filter `loops` times; result is in dst.

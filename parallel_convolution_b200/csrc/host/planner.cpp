@@ -23,11 +23,12 @@ constexpr int kRegionBytes = 512, kWarps = 16;
 double bytes_per_clk(int kind) {
     return kind == PCONV_KIND_SEP121 ? 20.0 : (kind == PCONV_KIND_INT ? 9.0 : 4.0);
 }
-constexpr double kClockGHz = 1.8, kLaunchUs = 4.0, kLoadBytesPerUsPerSm = 40e3;
-constexpr double kExchangeUs = 3.0, kExchangeUsPeer = 6.0;
-// split-phase resident kernel: what is left exposed of an exchange (issue time of the strip stores
-// and halo loads, the sibling hand-over)
-constexpr double kExchangeUsDual = 1.0, kExchangeUsDualPeer = 2.0;
+constexpr double kClockGHz = 1.9, kLaunchUs = 4.0, kLoadBytesPerUsPerSm = 40e3;
+// Persistent kernel (persist_kernel.cuh): what one exchange costs a CTA when nothing hides it (push +
+// release + flag round trip + bulk fetch), and what is left of it when a second CTA shares the SM and
+// computes meanwhile. Measured on B200 (profiles/README.md); only used to rank plans — the autotuner
+// measures the best few.
+constexpr double kExchangeUs = 1.6, kExchangeUsPeer = 4.5, kExchangeUsHidden = 0.35, kExchangeUsHiddenPeer = 1.5;
 
 int roundup(int v, int m) { return (v + m - 1) / m * m; }
 int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -41,15 +42,13 @@ extern "C" int pconv_plan(const pconv_plan_request_t* q, pconv_plan_t* out) {
     const double rate = bytes_per_clk(q->kind) * kClockGHz * 1e3;  // region bytes per us per SM
     int max_band = 0;
     for (int i = 0; i < q->nbands; ++i) max_band = std::max(max_band, q->bands[i]);
-    int kmax = std::min({loops, (kWarps * max_band - 1) / 2, (kRegionBytes / 2 - 64) / q->C});   // (upper bound)
+    const int warps = q->resident ? (q->warps == 8 ? 8 : kWarps) : kWarps;   // persistent CTAs: 8 or 16 warps
+    const int per_sm_cap = kWarps / warps;                                     // co-resident CTAs per SM
+    int kmax = std::min({loops, (warps * max_band - 1) / 2, (kRegionBytes / 2 - 64) / q->C});   // (upper bound)
     if (q->min_nbr_rows > 0) kmax = (int)std::min<int64_t>(kmax, q->min_nbr_rows);
     if (q->min_nbr_cols > 0) kmax = (int)std::min<int64_t>(kmax, q->min_nbr_cols);
     kmax = std::max(kmax, 1);
     const int k_lo = q->force_k > 0 ? q->force_k : 1, k_hi = q->force_k > 0 ? q->force_k : kmax;
-    const bool dual = q->resident && q->dual;
-    const int warps = (dual && q->dual == 2) ? kWarps - 1 : kWarps;   // protocol-warp variant: 15 compute warps
-    const double t_x = dual ? (q->peers ? kExchangeUsDualPeer : kExchangeUsDual)
-                            : (q->peers ? kExchangeUsPeer : kExchangeUs);
     bool found = false;
     double best = 0.0;
     for (int k = k_lo; k <= k_hi; ++k) {
@@ -61,28 +60,30 @@ extern "C" int pconv_plan(const pconv_plan_request_t* q, pconv_plan_t* out) {
             if (q->force_R > 0 && R != q->force_R) continue;
             const int RH = warps * R, th_max = RH - 2 * k;
             if (th_max < (q->resident ? k : 1)) continue;
-            int64_t nty = ceil_div(q->tile_rows, th_max);
-            if (dual) nty += nty & 1;                       // two virtual tile rows per CTA
-            if (q->resident && ntx * nty > (dual ? 2 : 1) * (int64_t)sms) continue;   // every CTA co-resident
-            if (dual && (nty + 2) * (ntx + 2) > 1024) continue;   // CTA flag pad
+            const int64_t nty = ceil_div(q->tile_rows, th_max);
+            if (q->resident && ntx * nty > (int64_t)per_sm_cap * sms) continue;   // every CTA co-resident
+            if (q->resident && ntx * nty > 1024) continue;                         // flag area (xplan.h)
             int TH = (int)ceil_div(q->tile_rows, nty);      // balance rows over the same tile count
             if (q->resident) TH = std::max(TH, k);
             if (q->resident) {
-                // A CTA only awaits the flags of its eight surrounding CTAs: with a rank below / to the
-                // right, the last CTA row / column must itself be at least one halo deep, or the halo of
-                // the row / column before it would reach past it into that rank unsynchronised.
+                // A CTA exchanges with its eight surrounding CTAs only: with a rank below / to the right,
+                // the last CTA row / column must itself be at least one halo deep, or the halo of the row
+                // / column before it would reach past it into that rank; across ranks whole chunks move.
+                if (ceil_div(q->tile_rows, TH) != nty) continue;
                 const int64_t last_rows = q->tile_rows - (nty - 1) * (int64_t)TH;
                 const int64_t last_cb = q->tile_cb - (ntx - 1) * (int64_t)TWB;
                 if (q->min_nbr_rows > 0 && last_rows < k) continue;
-                if (q->min_nbr_cols > 0 && last_cb < (int64_t)k * q->C) continue;
+                if (q->min_nbr_cols > 0 && (last_cb < HB || (q->tile_cb & 15))) continue;
             }
-            const int64_t waves = ceil_div(dual ? ntx * nty / 2 : ntx * nty, sms);
+            const int64_t waves = ceil_div(ntx * nty, sms);
             double total, per_launch;
             if (q->resident) {
                 const int64_t nblocks = ceil_div(loops, k);
-                const double regions = dual ? 2.0 : 1.0;     // per CTA, computed back to back
-                total = kLaunchUs + regions * (RH * (double)kRegionBytes + (double)TH * TWB) / kLoadBytesPerUsPerSm +
-                        nblocks * regions * (k * RH * (double)kRegionBytes / rate) + (nblocks - 1) * regions * t_x;
+                const double on_sm = (double)ceil_div(ntx * nty, sms);       // CTAs sharing the busiest SM
+                const double t_x = on_sm > 1.0 ? (q->peers ? kExchangeUsHiddenPeer : kExchangeUsHidden)
+                                               : (q->peers ? kExchangeUsPeer : kExchangeUs);
+                total = kLaunchUs + on_sm * (RH * (double)kRegionBytes + (double)TH * TWB) / kLoadBytesPerUsPerSm +
+                        (double)loops * on_sm * (RH * (double)kRegionBytes / rate) + (nblocks - 1) * on_sm * t_x;
                 per_launch = total;
             } else {
                 const double t_tile = RH * (double)kRegionBytes / kLoadBytesPerUsPerSm +

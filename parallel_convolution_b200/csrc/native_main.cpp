@@ -110,9 +110,21 @@ int main(int argc, char** argv) {
         pconv_plan_request_t q{};
         q.tile_rows = H; q.tile_cb = rb; q.C = C; q.kind = f.kind; q.loops = loops > 0 ? loops : 1;
         q.sms = pconv_cuda_sm_count();
-        q.nbands = pconv_stream_band_heights(f.kind, q.bands, 8);
+        q.nbands = pconv_stream_band_heights(f.kind, q.bands, 16);
         pconv_plan_t plan{};
         if (pconv_plan(&q, &plan) != 0) { std::fprintf(stderr, "pconv_native: no launch plan\n"); return EXIT_FAILURE; }
+        // the persistent kernel (one launch, the image stays in registers) when the image fits on chip
+        pconv_plan_request_t qp = q;
+        qp.resident = 1;
+        qp.nbands = pconv_persist_band_heights(f.kind, qp.bands, 16);
+        pconv_plan_t pplan{};
+        int pwarps = 0;
+        double pbest = 0.0;
+        for (int w = 8; w <= 16 && loops > 0; w += 8) {
+            qp.warps = w;
+            pconv_plan_t cand{};
+            if (pconv_plan(&qp, &cand) == 0 && (!pwarps || cand.est_us < pbest)) { pplan = cand; pwarps = w; pbest = cand.est_us; }
+        }
         const int64_t pitch = (rb + 127) / 128 * 128;
         void *bufA = nullptr, *bufB = nullptr, *stream = nullptr, *e0 = nullptr, *e1 = nullptr;
         CK(pconv_cuda_malloc(&bufA, H * pitch + 256));
@@ -134,18 +146,32 @@ int main(int argc, char** argv) {
         }
         std::vector<int32_t> ks;
         for (int done = 0; done < loops; done += plan.k) ks.push_back(std::min(plan.k, loops - done));
-        CK(pconv_kernel_prepare(f.kind, C, plan.R, 0));   // one-time module load stays out of the loop time
+        pconv_persist_params_t ps;
+        std::memset(&ps, 0, sizeof(ps));
+        void* arena = nullptr;
+        if (pwarps) {
+            ps.g = pp[0].g; ps.src[4] = (const uint8_t*)bufA; ps.dst = (uint8_t*)bufB; ps.filt = f;
+            ps.loops = loops; ps.k = pplan.k; ps.TH = pplan.TH; ps.TWB = pplan.TWB; ps.HB = pplan.HB;
+            ps.R = pplan.R; ps.W = pwarps; ps.nty = pplan.nty; ps.ntx = pplan.ntx;
+            ps.arena_bytes = pconv_persist_arena_bytes(&ps);
+            if (ps.arena_bytes <= 0 || pconv_cuda_malloc(&arena, ps.arena_bytes) != 0) pwarps = 0;
+            ps.arena[4] = (uint8_t*)arena;
+            if (pwarps && pconv_persist_capacity(&ps) < pplan.nty * pplan.ntx) pwarps = 0;   // also loads the module
+        }
+        if (!pwarps) CK(pconv_kernel_prepare(f.kind, C, plan.R));   // one-time module load stays out of the loop time
         CK(pconv_cuda_stream_sync(stream));               // ... and so does the H2D copy (as in the reference's MPI timer)
         CK(pconv_cuda_event_record(e0, stream));
-        if (!ks.empty()) CK(pconv_stream_run(pp, 1, ks.data(), (int)ks.size(), 0, 0, 0, nullptr, stream));
+        if (pwarps) CK(pconv_persist_launch(&ps, stream));
+        else if (!ks.empty()) CK(pconv_stream_run(pp, 1, ks.data(), (int)ks.size(), 0, 0, 0, nullptr, stream));
         CK(pconv_cuda_event_record(e1, stream));
-        void* final_buf = (ks.size() & 1) ? bufB : bufA;   // parity-correct for any loops (defect D4)
+        void* final_buf = (pwarps || (ks.size() & 1)) ? bufB : bufA;   // parity-correct for any loops (defect D4)
         CK(pconv_cuda_memcpy2d_async(result.data(), rb, final_buf, pitch, rb, H, 2, stream));
         CK(pconv_cuda_stream_sync(stream));
         float ms = 0.f;
         CK(pconv_cuda_event_elapsed_ms(e0, e1, &ms));
         loop_s = ms / 1e3;
         pconv_cuda_free(bufA); pconv_cuda_free(bufB);
+        if (arena) pconv_cuda_free(arena);
     }
     if (pconv_create_file(out.c_str(), nbytes) != 0 ||
         pconv_write_rect(out.c_str(), rb, 0, H, 0, rb, result.data(), rb) != 0) {

@@ -40,7 +40,8 @@ class EngineConfig:
     workers: int | None = None       # single-process: number of virtual ranks (default 1)
     grid: tuple[int, int] | None = None
     halo_depth: int | None = None    # temporal-blocking depth k (None: planner decides)
-    mode: str = "auto"               # fused backend: auto | stream | resident | resident2
+    mode: str = "auto"               # fused backend: auto | stream | resident (persistent kernel)
+    warps: int | None = None         # persistent kernel: warps per CTA (8 | 16; None: planner/autotuner)
     threads: int = 0                 # cpu backend: OpenMP threads per rank
     device: int | None = None        # CUDA device index (default: LOCAL_RANK or 0)
     timeout_ms: float = 10_000.0     # in-kernel watchdog for neighbour flags
@@ -139,7 +140,7 @@ class ConvEngine:
             from .parallel.fused_runtime import FusedRuntime
             self._impl = FusedRuntime(self.grid, self.filter, self.rank, self.world, self.dist,
                                       halo_depth=cfg.halo_depth, mode=cfg.mode,
-                                      timeout_ms=cfg.timeout_ms, slots=cfg.slots)
+                                      timeout_ms=cfg.timeout_ms, slots=cfg.slots, warps=cfg.warps)
         else:
             from .parallel.nccl_backend import NcclRuntime
             self._impl = NcclRuntime(self.grid, self.filter, self.rank, self.world, self.dist,

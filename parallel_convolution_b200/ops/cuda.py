@@ -18,10 +18,20 @@ SELF = 4
 # Persistent kernels of several virtual ranks must run CONCURRENTLY (they spin on each other's flags).
 # Streams are multiplexed onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); two rank
 # streams sharing a queue serialise their kernels behind each other's event records — a deadlock that
-# only the watchdog ends. The variable is read when the CUDA context is created, so set it before the
-# library makes its first CUDA call (no effect if another library already initialised CUDA).
+# only the watchdog ends.
 MAX_CONNECTIONS = 32
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", str(MAX_CONNECTIONS))
+
+
+def usable_connections() -> int:
+    """Hardware queues concurrent streams can count on. CUDA_DEVICE_MAX_CONNECTIONS is read when the CUDA
+    context is created (default 8): the package never sets it behind the user's back — export it (up to
+    32) before the first CUDA call to run more virtual ranks with the persistent kernel; with fewer
+    usable queues than virtual ranks the runtime falls back to the streaming kernel."""
+    try:
+        v = int(os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS", "8"))
+    except ValueError:
+        v = 8
+    return max(1, min(v, MAX_CONNECTIONS))
 
 
 class Geometry(C.Structure):
@@ -45,13 +55,12 @@ class StreamParams(C.Structure):
                 ("sync", Sync)]
 
 
-class ResidentParams(C.Structure):
-    _fields_ = [("g", Geometry), ("src_a", C.c_void_p * 9), ("src_b", C.c_void_p * 9),
-                ("self_a", C.c_void_p), ("self_b", C.c_void_p), ("filt", FilterSpec),
+class PersistParams(C.Structure):
+    _fields_ = [("g", Geometry), ("src", C.c_void_p * 9), ("dst", C.c_void_p), ("filt", FilterSpec),
                 ("loops", C.c_int32), ("k", C.c_int32), ("TH", C.c_int32), ("TWB", C.c_int32),
-                ("HB", C.c_int32), ("R", C.c_int32), ("nty", C.c_int32), ("ntx", C.c_int32),
-                ("cta_flags", C.c_void_p), ("remote_cta_flags", C.c_void_p * 9),
-                ("epoch_base", C.c_uint32), ("dual", C.c_uint32), ("sync", Sync)]
+                ("HB", C.c_int32), ("R", C.c_int32), ("W", C.c_int32), ("nty", C.c_int32),
+                ("ntx", C.c_int32), ("arena", C.c_void_p * 9), ("arena_bytes", C.c_int64),
+                ("epoch_base", C.c_uint32), ("peer_scope", C.c_uint32), ("sync", Sync)]
 
 
 class CudaError(RuntimeError):
@@ -67,10 +76,13 @@ def lib() -> C.CDLL:
     L.pconv_stream_run.argtypes = [C.POINTER(StreamParams), C.c_int, C.POINTER(C.c_int32), C.c_int,
                                    C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_void_p), vp]
     L.pconv_sync_launch.argtypes = [C.POINTER(Sync), vp]
-    L.pconv_kernel_prepare.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+    L.pconv_kernel_prepare.argtypes = [C.c_int, C.c_int, C.c_int]
     L.pconv_stream_band_heights.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int]
-    if hasattr(L, "pconv_resident_launch"):
-        L.pconv_resident_launch.argtypes = [C.POINTER(ResidentParams), vp]
+    L.pconv_persist_launch.argtypes = [C.POINTER(PersistParams), vp]
+    L.pconv_persist_arena_bytes.argtypes = [C.POINTER(PersistParams)]
+    L.pconv_persist_arena_bytes.restype = i64
+    L.pconv_persist_capacity.argtypes = [C.POINTER(PersistParams)]
+    L.pconv_persist_band_heights.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int]
     L.pconv_cuda_set_device.argtypes = [C.c_int]
     L.pconv_cuda_l2_bytes.restype = i64
     L.pconv_cuda_last_error.restype = C.c_char_p
@@ -144,23 +156,10 @@ def band_heights(kind: int) -> list[int]:
     return [int(buf[i]) for i in range(n)]
 
 
-def resident2_band_heights(kind: int) -> list[int]:
-    """Band heights (rows per warp per virtual tile) compiled for the split-phase resident kernel."""
-    L = lib()
-    if not hasattr(L, "pconv_resident2_band_heights"):
-        return []
+def persist_band_heights(kind: int) -> list[int]:
+    """Band heights compiled for the persistent kernel (the same list for 8 and 16 warps per CTA)."""
     buf = (C.c_int * 16)()
-    n = int(L.pconv_resident2_band_heights(kind, buf, 16))
-    return [int(buf[i]) for i in range(n)]
-
-
-def resident3_band_heights(kind: int) -> list[int]:
-    """Band heights compiled for the split-phase resident kernel with a protocol warp (experimental)."""
-    L = lib()
-    if not hasattr(L, "pconv_resident3_band_heights"):
-        return []
-    buf = (C.c_int * 16)()
-    n = int(L.pconv_resident3_band_heights(kind, buf, 16))
+    n = int(lib().pconv_persist_band_heights(kind, buf, 16))
     return [int(buf[i]) for i in range(n)]
 
 
@@ -292,10 +291,9 @@ def unpack_rect(tile: int, pitch: int, row0: int, byte0: int, rows: int, nbytes:
            "unpack_rect")
 
 
-def kernel_prepare(kind: int, channels: int, band: int, resident: bool | int = False) -> None:
-    """``resident``: False/0 stream kernel, True/1 resident kernel, 2 split-phase resident kernel,
-    3 split-phase + protocol warp."""
-    _check(lib().pconv_kernel_prepare(kind, channels, band, int(resident)), "kernel_prepare")
+def kernel_prepare(kind: int, channels: int, band: int) -> None:
+    """Force the module load of a stream-kernel instance (the persistent kernel: ``persist_capacity``)."""
+    _check(lib().pconv_kernel_prepare(kind, channels, band), "kernel_prepare")
 
 
 def stream_launch(p: StreamParams, stream: int) -> None:
@@ -315,5 +313,21 @@ def sync_launch(s: Sync, stream: int) -> None:
     _check(lib().pconv_sync_launch(C.byref(s), stream), "sync_launch")
 
 
-def resident_launch(p: ResidentParams, stream: int) -> None:
-    _check(lib().pconv_resident_launch(C.byref(p), stream), "resident_launch")
+def persist_launch(p: PersistParams, stream: int) -> None:
+    _check(lib().pconv_persist_launch(C.byref(p), stream), "persist_launch")
+
+
+def persist_arena_bytes(p: PersistParams) -> int:
+    """Exchange-arena bytes the plan in ``p`` needs."""
+    n = int(lib().pconv_persist_arena_bytes(C.byref(p)))
+    if n < 0:
+        _check(n, "persist_arena_bytes")
+    return n
+
+
+def persist_capacity(p: PersistParams) -> int:
+    """CTAs of the plan's kernel instance the device keeps resident (loads the module as a side effect)."""
+    n = int(lib().pconv_persist_capacity(C.byref(p)))
+    if n < 0:
+        _check(n, "persist_capacity")
+    return n

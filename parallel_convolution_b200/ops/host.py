@@ -34,9 +34,9 @@ class FilterSpec(C.Structure):
 class PlanRequest(C.Structure):
     _fields_ = [("tile_rows", C.c_int64), ("tile_cb", C.c_int64), ("min_nbr_rows", C.c_int64),
                 ("min_nbr_cols", C.c_int64), ("C", C.c_int32), ("kind", C.c_int32),
-                ("loops", C.c_int32), ("sms", C.c_int32), ("bands", C.c_int32 * 8),
+                ("loops", C.c_int32), ("sms", C.c_int32), ("bands", C.c_int32 * 16),
                 ("nbands", C.c_int32), ("force_k", C.c_int32), ("force_R", C.c_int32),
-                ("resident", C.c_int32), ("peers", C.c_int32), ("dual", C.c_int32)]
+                ("resident", C.c_int32), ("peers", C.c_int32), ("warps", C.c_int32)]
 
 
 class PlanResult(C.Structure):
@@ -58,6 +58,8 @@ def lib() -> C.CDLL:
     L.pconv_split.argtypes = [i64, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)]
     L.pconv_split.restype = None
     L.pconv_oracle_run.argtypes = [u8p, u8p, u8p, i64, i64, C.c_int, fsp, C.c_int]
+    L.pconv_xplan_emulate.argtypes = [u8p, u8p, i64, i64, C.c_int, fsp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, C.c_uint32]
     L.pconv_cpu_convolve.argtypes = [u8p, u8p, i64, C.c_int, fsp, i64, i64, i64, i64, C.c_int]
     L.pconv_cpu_run_image.argtypes = [u8p, u8p, i64, i64, C.c_int, fsp, C.c_int, C.c_int]
     L.pconv_cpu_run_image_blocked.argtypes = [u8p, u8p, i64, i64, C.c_int, fsp, C.c_int, C.c_int, C.c_int]
@@ -116,16 +118,16 @@ def split(extent: int, parts: int, idx: int) -> tuple[int, int]:
 def plan(tile_rows: int, tile_cb: int, Cn: int, kind: int, loops: int, bands: list[int], *,
          min_nbr_rows: int = 0, min_nbr_cols: int = 0, sms: int = 148, force_k: int = 0,
          force_R: int = 0, resident: bool = False, peers: bool = False,
-         dual: bool | int = False) -> PlanResult | None:
+         warps: int = 16) -> PlanResult | None:
     """Native launch planner (csrc/host/planner.cpp). None when no plan is feasible."""
     q = PlanRequest()
     q.tile_rows, q.tile_cb, q.min_nbr_rows, q.min_nbr_cols = tile_rows, tile_cb, min_nbr_rows, min_nbr_cols
     q.C, q.kind, q.loops, q.sms = Cn, kind, loops, sms
-    for i, b in enumerate(bands[:8]):
+    for i, b in enumerate(bands[:16]):
         q.bands[i] = b
-    q.nbands = min(len(bands), 8)
+    q.nbands = min(len(bands), 16)
     q.force_k, q.force_R = force_k or 0, force_R or 0
-    q.resident, q.peers, q.dual = int(resident), int(peers), int(dual)
+    q.resident, q.peers, q.warps = int(resident), int(peers), int(warps)
     out = PlanResult()
     rc = lib().pconv_plan(C.byref(q), C.byref(out))
     if rc < 0:
@@ -143,6 +145,19 @@ def oracle(image: np.ndarray, f: FilterSpec, loops: int) -> np.ndarray:
     if rc != 0:
         raise RuntimeError(f"oracle failed ({rc})")
     return out
+
+
+def xplan_emulate(image: np.ndarray, f: FilterSpec, loops: int, grid: tuple[int, int], k: int, R: int,
+                  W: int, TH: int = 0, epoch_base: int = 0) -> np.ndarray | int:
+    """CPU replay of the persistent kernel's pushed halo exchange (csrc/host/xplan_emu.cpp): the result
+    image, or the negative code of a geometry the launcher rejects."""
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    H, Wpx = img.shape[:2]
+    Cn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.zeros_like(img)
+    rc = lib().pconv_xplan_emulate(_ptr(img), _ptr(out), H, Wpx, Cn, C.byref(f), loops, grid[0], grid[1],
+                                   k, R, W, TH, epoch_base)
+    return out if rc == 0 else int(rc)
 
 
 def cpu_run_image(image: np.ndarray, f: FilterSpec, loops: int, threads: int = 0) -> np.ndarray:

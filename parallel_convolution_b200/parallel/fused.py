@@ -1,11 +1,13 @@
-"""Fused stencil + halo backend (the product): drives ``stream_kernel`` / ``resident_kernel``.
+"""Fused stencil + halo backend (the product): drives ``stream_kernel`` / ``persist_kernel``.
 
-One *tile driver* per rank owns two ping-pong tile buffers, a flag pad and a status block in
-plain ``cudaMalloc`` memory (IPC-exportable, see ``peer_memory.py``). A launch gets the base
-pointers of the up-to-eight neighbouring tiles; the kernel pulls halo rows / columns / corners
-straight out of those buffers (NVLink P2P loads across GPUs) and synchronises with per-launch
-epoch flags written by the neighbours with ``st.release.sys``. There is no NCCL and no host
-round trip on this path; the host enqueues every launch of a run up front.
+One *tile driver* per rank owns two ping-pong tile buffers, a flag pad, a status block and an
+*exchange arena* in plain ``cudaMalloc`` memory (IPC-exportable, see ``peer_memory.py``). A streaming
+launch gets the base pointers of the up-to-eight neighbouring tiles; the kernel pulls halo rows /
+columns / corners straight out of those buffers (NVLink P2P loads across GPUs) and synchronises with
+per-launch epoch flags written by the neighbours with ``st.release.sys``. The persistent kernel keeps
+the tile in registers for a whole run and its CTAs *push* their borders into the neighbours' inbox
+slots inside the arenas (NVLink P2P stores across GPUs). There is no NCCL and no host round trip on
+this path; the host enqueues every launch of a run up front.
 
 Replaces the reference's ``MPI_Isend/Irecv`` + ``MPI_Wait`` iteration loop
 (``mpi/mpi_conv.c:164-248``) for the GPU path.
@@ -25,14 +27,19 @@ from ..ops import cuda as K
 from .decomposition import TileGrid
 from .plan import StreamPlan, plan_stream
 
+import os
+
 FLAG_BYTES = 256      # bank 0 (+0): launch epochs, bank 1 (+64): "input ready" step counters
 BANK1 = 64
-STATUS_WORDS = 11     # u64: error, max wait ns, sum wait ns, waits, probe: publish/wait/reload/compute ns, exchanges,
-                      # first timed-out wait of the split-phase kernel (packed vi/tj/dir/epoch), flag value seen
-CTA_FLAG_BYTES = 4096  # resident kernel: (nty+2)*(ntx+2) u32 epochs, nty*ntx <= #SMs
-# control block layout (one cudaMalloc, one IPC handle): flags | counter | status | cta_flags
-OFF_COUNTER, OFF_STATUS, OFF_CTA = FLAG_BYTES, FLAG_BYTES + 64, FLAG_BYTES + 64 + 128
-CTL_BYTES = OFF_CTA + CTA_FLAG_BYTES
+STATUS_WORDS = 9      # u64: error, max wait ns, sum wait ns, waits; persistent-kernel probe CTA: push /
+                      # signal+wait / inbox->register / compute ns, exchanges
+# control block layout (one cudaMalloc, one IPC handle): flags | counter | status
+OFF_COUNTER, OFF_STATUS = FLAG_BYTES, FLAG_BYTES + 64
+CTL_BYTES = OFF_STATUS + 128
+# Exchange arena of the persistent kernel (csrc/common/xplan.h): 64 KB of per-CTA flag words + two
+# parities of one inbox slot per CTA. Fixed size so that it can be IPC-mapped once; plans whose slots
+# do not fit are not offered (a 1920x2520 RGB image on one GPU needs 5 MB).
+ARENA_BYTES = int(os.environ.get("PCONV_ARENA_MIB", "48")) << 20
 
 
 def tile_pitch(grid: TileGrid) -> int:
@@ -51,7 +58,7 @@ class RankMemory:
     status: int = 0
     nbytes: int = 0
     owned: bool = True
-    cta_flags: int = 0
+    arena: int = 0
 
     @staticmethod
     def allocate(rows: int, pitch: int, slots: int = 1) -> "RankMemory":
@@ -60,19 +67,21 @@ class RankMemory:
         nbytes = rows * pitch + 256
         bufs = [K.malloc(nbytes) for _ in range(2 * slots)]
         ctl = K.malloc(CTL_BYTES)
-        return RankMemory(bufs, ctl, ctl + OFF_COUNTER, ctl + OFF_STATUS, nbytes, True, ctl + OFF_CTA)
+        return RankMemory(bufs, ctl, ctl + OFF_COUNTER, ctl + OFF_STATUS, nbytes, True, K.malloc(ARENA_BYTES))
 
     @staticmethod
-    def view(bufs: list[int], ctl: int, nbytes: int) -> "RankMemory":
+    def view(bufs: list[int], ctl: int, nbytes: int, arena: int = 0) -> "RankMemory":
         """Peer-mapped view of another rank's memory (same control-block layout)."""
-        return RankMemory(bufs, ctl, ctl + OFF_COUNTER, ctl + OFF_STATUS, nbytes, False, ctl + OFF_CTA)
+        return RankMemory(bufs, ctl, ctl + OFF_COUNTER, ctl + OFF_STATUS, nbytes, False, arena)
 
     def free(self) -> None:
         if self.owned:
             for p in self.bufs:
                 K.free(p)
             K.free(self.flags)
-        self.bufs, self.flags = [], 0
+            if self.arena:
+                K.free(self.arena)
+        self.bufs, self.flags, self.arena = [], 0, 0
 
 
 @dataclass
@@ -142,25 +151,26 @@ class TileDriver:
         p.sync.inject_drop_signal = 1 if self.inject_drop_signal else 0
         return p
 
-    def resident_params(self, plan: StreamPlan, loops: int, src_parity: int, wait: int, signal: int,
-                        cta_epoch: int, slot: int = 0, wait_bank1: bool = False) -> K.ResidentParams:
-        p = K.ResidentParams()
+    def persist_params(self, plan: StreamPlan, loops: int, src_parity: int, wait: int, signal: int,
+                       cta_epoch: int, slot: int = 0, wait_bank1: bool = False,
+                       peer_scope: bool = False) -> K.PersistParams:
+        """One launch of the persistent kernel: reads buffer ``src_parity`` (and the neighbours'), writes
+        the other buffer of the pair; exchange b carries epoch ``cta_epoch + b``."""
+        p = K.PersistParams()
         p.g = self._geom
         src_parity += 2 * slot
         for d in range(9):
             nb = self.neighbors[d]
-            p.src_a[d] = nb.bufs[src_parity] if nb is not None else None
-            p.src_b[d] = nb.bufs[src_parity ^ 1] if nb is not None else None
-            remote = nb is not None and d != 4 and nb is not self.mem
-            p.remote_cta_flags[d] = nb.cta_flags if remote else None
+            p.src[d] = nb.bufs[src_parity] if nb is not None else None
+            p.arena[d] = nb.arena if nb is not None else None
             p.sync.remote_flags[d] = (nb.flags + 4 * (8 - d)) if (nb is not None and d != 4) else None
-        p.self_a, p.self_b = self.mem.bufs[src_parity], self.mem.bufs[src_parity ^ 1]
+        p.dst = self.mem.bufs[src_parity ^ 1]
+        p.arena_bytes = ARENA_BYTES
         p.filt = self.filt.spec
-        p.loops, p.k, p.TH, p.TWB, p.HB, p.R = loops, plan.k, plan.TH, plan.TWB, plan.HB, plan.R
+        p.loops, p.k, p.TH, p.TWB, p.HB, p.R, p.W = loops, plan.k, plan.TH, plan.TWB, plan.HB, plan.R, plan.W
         p.nty, p.ntx = plan.nty, plan.ntx
-        p.dual = 1 if plan.dual else 0
-        p.cta_flags = self.mem.cta_flags
-        p.epoch_base = cta_epoch
+        p.epoch_base = cta_epoch & 0xFFFFFFFF
+        p.peer_scope = 1 if peer_scope else 0
         p.sync.local_flags = self.mem.flags + (BANK1 if wait_bank1 else 0)
         p.sync.done_counter = self.mem.counter
         p.sync.status = self.mem.status
@@ -215,21 +225,17 @@ class TileDriver:
         self.probe = {"publish_us": float(out[4]) / 1e3, "wait_us": float(out[5]) / 1e3,
                       "reload_us": float(out[6]) / 1e3, "compute_us": float(out[7]) / 1e3,
                       "exchanges": int(out[8])}
-        if out[9]:
-            w = int(out[9])
-            self.probe["timed_out_wait"] = {"vi": (w >> 48) & 0x7fff, "tj": (w >> 40) & 0xff, "dir": (w >> 32) & 0xff,
-                                            "epoch": w & 0xffffffff, "flag_seen": int(out[10])}
         return bool(out[0]), float(out[1]) / 1e3, float(out[2]) / 1e3, int(out[3])
 
 
-def make_resident_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int | None = None,
-                       sms: int | None = None, bands: list[int] | None = None,
-                       band: int | None = None, peers: bool = False, dual: bool | int = False) -> StreamPlan | None:
-    """Plan for the persistent resident kernel (``dual``: its split-phase variant), or None when the
-    tile does not fit on chip."""
-    from .plan import plan_resident
+def make_persist_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int | None = None,
+                      sms: int | None = None, bands: list[int] | None = None,
+                      band: int | None = None, peers: bool = False, warps: int = 8) -> StreamPlan | None:
+    """Plan for the persistent kernel with ``warps`` warps per CTA, or None when the tile does not fit
+    on chip (or its inbox slots do not fit the exchange arena)."""
+    from .plan import plan_persist
     if not grid.exact and grid.workers > 1:
-        return None      # the mirrored CTA-flag rings assume identical tile shapes on every rank
+        return None      # CTA coordinates wrap into the neighbouring rank: identical tile shapes everywhere
     Cn = grid.channels
     multi_r, multi_c = grid.grid_rows > 1, grid.grid_cols > 1
     kw = {}
@@ -237,10 +243,21 @@ def make_resident_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int
         kw["sms"] = sms
     if bands:
         kw["bands"] = bands
-    return plan_resident(grid.max_tile_rows(), grid.max_tile_cols() * Cn, Cn, filt.kind, max(loops, 1),
-                         min_nbr_rows=grid.min_tile_rows() if multi_r else None,
-                         min_nbr_cols=grid.min_tile_cols() if multi_c else None,
-                         force_k=halo_depth, force_R=band, peers=peers, dual=dual, **kw)
+    p = plan_persist(grid.max_tile_rows(), grid.max_tile_cols() * Cn, Cn, filt.kind, max(loops, 1),
+                     min_nbr_rows=grid.min_tile_rows() if multi_r else None,
+                     min_nbr_cols=grid.min_tile_cols() if multi_c else None,
+                     force_k=halo_depth, force_R=band, peers=peers, warps=warps, **kw)
+    if p is not None and persist_arena_bytes(p) > ARENA_BYTES:
+        return None
+    return p
+
+
+def persist_arena_bytes(p: StreamPlan) -> int:
+    """csrc/common/xplan.h: 64 KB of flags + 2 parities x CTAs x slot (blocks N,S | W,E | 4 corners)."""
+    nh, nc = p.HB // 16, p.TWB // 16
+    chunks = 2 * p.k * nc + 2 * p.TH * nh + 4 * p.k * nh
+    chunks = (chunks + 7) & ~7
+    return 1024 * 64 + 2 * p.nty * p.ntx * chunks * 16
 
 
 def make_plan(grid: TileGrid, filt: Filter, loops: int, halo_depth: int | None = None,
@@ -269,11 +286,12 @@ class VirtualCluster:
     """
 
     def __init__(self, grid: TileGrid, filt: Filter, halo_depth: int | None = None,
-                 band: int | None = None, mode: str = "stream", timeout_ms: float = 10_000.0):
+                 band: int | None = None, mode: str = "stream", timeout_ms: float = 10_000.0,
+                 warps: int | None = None):
         from .fused_runtime import FusedRuntime
         self.grid = grid
         self.rt = FusedRuntime(grid, filt, 0, 1, None, halo_depth=halo_depth, band=band, mode=mode,
-                               timeout_ms=timeout_ms)
+                               timeout_ms=timeout_ms, warps=warps)
         self.sms, self.bands = self.rt.sms, self.rt.bands
 
     def close(self) -> None:

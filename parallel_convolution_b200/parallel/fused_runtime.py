@@ -7,9 +7,13 @@ Unifies the two process models behind one interface used by ``ConvEngine``:
 * one process per GPU — ``world > 1``: this process owns tile ``rank`` and maps its neighbours'
   buffers through CUDA IPC (``peer_memory.PeerGroup``).
 
-A run is enqueued with ONE native call (``pconv_stream_run``): all launches of all local tiles go
-onto one stream back to back; cross-rank ordering is entirely in-kernel (epoch flags). The host
-synchronises twice per run (before: inputs in place; after: results readable), never in between.
+Two kernels drive a run (``mode``): ``"resident"`` — ONE cooperative launch of the persistent kernel
+(``persist_kernel.cuh``: the tile stays in registers, CTAs push their borders into each other's inbox
+slots every k iterations, across GPUs through the peer-mapped exchange arenas) whenever the tile fits
+on chip — and ``"stream"`` (``stream_kernel.cuh``: k fused iterations per launch over tiles of any
+size, all launches of a run enqueued by one native call). Cross-rank ordering is entirely in-kernel
+(epoch flags). The host synchronises twice per run (before: inputs in place; after: results readable),
+never in between.
 """
 from __future__ import annotations
 
@@ -20,21 +24,22 @@ import numpy as np
 from ..models.filters import Filter
 from ..ops import cuda as K
 from .decomposition import TileGrid
-from .fused import (RankMemory, TileDriver, make_plan, make_resident_plan,
-                    tile_pitch)
+from .fused import (RankMemory, TileDriver, make_persist_plan, make_plan, tile_pitch)
 from .plan import StreamPlan
 
-# Whether "auto" lets the autotuner try the split-phase resident kernel (explicit --mode resident2
-# always works). Single-GPU runs only until it has been validated across NVLink.
-AUTO_RESIDENT2 = os.environ.get("PCONV_RESIDENT2", "0") == "1"
+MODES = ("stream", "resident")
 
 
 class FusedRuntime:
     def __init__(self, grid: TileGrid, filt: Filter, rank: int, world: int, dist,
                  halo_depth: int | None = None, mode: str = "auto", timeout_ms: float = 10_000.0,
-                 band: int | None = None, slots: int = 1):
+                 band: int | None = None, slots: int = 1, warps: int | None = None):
+        if mode not in ("auto",) + MODES:
+            raise ValueError(f"unknown kernel mode {mode!r} (auto | stream | resident)")
+        if warps not in (None, 8, 16):
+            raise ValueError("warps per CTA of the persistent kernel: 8 or 16")
         self.grid, self.filt, self.rank, self.world, self.dist = grid, filt, rank, world, dist
-        self.halo_depth, self.mode, self.band = halo_depth, mode, band
+        self.halo_depth, self.mode, self.band, self.warps = halo_depth, mode, band, warps
         self.pitch = tile_pitch(grid)
         self.slots, self.slot = max(1, int(slots)), 0
         self._pipe = None
@@ -42,8 +47,7 @@ class FusedRuntime:
         self.stream = K.stream_create()
         self.sms = K.sm_count()
         self.bands = K.band_heights(filt.kind)
-        self.bands2 = K.resident2_band_heights(filt.kind)    # split-phase resident kernel
-        self.bands3 = K.resident3_band_heights(filt.kind)    # ... with a protocol warp (experimental)
+        self.pbands = K.persist_band_heights(filt.kind)
         rows = grid.max_tile_rows()
         self.peers = None
         if world > 1:
@@ -64,16 +68,16 @@ class FusedRuntime:
                                       timeout_ms) for r in self.local_ranks}
         self.parity = 0
         self.epoch = 0
-        self.cta_epoch = 0            # resident kernel: per-CTA exchange epochs (monotonic)
+        self.cta_epoch = 0            # persistent kernel: per-CTA exchange epochs (monotonic, contiguous)
         self.multi = grid.workers > 1
         self._plans: dict[int, StreamPlan] = {}
-        self._rplans: dict[int, StreamPlan | None] = {}
-        self._r2plans: dict[int, StreamPlan | None] = {}
-        self._r3plans: dict[int, StreamPlan | None] = {}
-        # virtual ranks in resident mode need their persistent kernels co-resident: one stream each,
-        # and no two of them on one hardware queue (ops.cuda.MAX_CONNECTIONS) — beyond that, stream mode
+        self._pplans: dict[int, StreamPlan | None] = {}
+        self._tuned: dict[int, str] = {}
+        # Virtual ranks in resident mode need their persistent kernels co-resident: one stream each, and
+        # no two of them on one hardware queue. CUDA multiplexes streams onto CUDA_DEVICE_MAX_CONNECTIONS
+        # queues (read when the context is created); beyond what is usable, stream mode only.
         self._rank_streams = ({r: K.stream_create() for r in self.local_ranks}
-                              if 1 < len(self.local_ranks) < K.MAX_CONNECTIONS - 2 else {})
+                              if 1 < len(self.local_ranks) <= K.usable_connections() - 2 else {})
 
     # -- lifecycle ------------------------------------------------------------------------------
     def close(self) -> None:
@@ -143,86 +147,92 @@ class FusedRuntime:
         self._first_wait = self.epoch
         return len(self.drivers)
 
-    def resident_plan(self, loops: int, dual: bool | int = False) -> StreamPlan | None:
-        """Plan of the persistent kernel (``dual``: 1/True its split-phase variant, 2 the split-phase
-        variant with a protocol warp); None if it cannot hold the tile."""
-        dual = int(dual)
-        cache = (self._rplans, self._r2plans, self._r3plans)[dual]
+    def resident_plan(self, loops: int) -> StreamPlan | None:
+        """Plan of the persistent kernel (the cheaper of 8 / 16 warps per CTA by the model, unless
+        ``warps`` pins it); None if the tile does not fit on chip or the geometry is not supported."""
         if len(self.local_ranks) > 1 and not self._rank_streams:
             return None        # too many virtual ranks for concurrent persistent kernels
-        if loops not in cache:
-            nloc = len(self.local_ranks)
-            bands = (self.bands, self.bands2, self.bands3)[dual]
-            if dual and (not bands or (self.band and self.band not in bands)):
-                cache[loops] = None
-            else:
-                cache[loops] = make_resident_plan(
-                    self.grid, self.filt, loops, self.halo_depth, self.sms // nloc, bands, self.band,
-                    peers=self.world > 1, dual=dual)
-        return cache[loops]
+        if loops not in self._pplans:
+            best = None
+            for w in ((self.warps,) if self.warps else (8, 16)):
+                p = self._persist_candidate(loops, self.halo_depth, self.band, w)
+                if p is not None and (best is None or p.est_us_per_launch < best.est_us_per_launch):
+                    best = p
+            self._pplans[loops] = best
+        return self._pplans[loops]
 
-    _VARIANT = {"stream": -1, "resident": 0, "resident2": 1, "resident3": 2}
+    def _persist_candidate(self, loops: int, k: int | None, R: int | None, warps: int) -> StreamPlan | None:
+        nloc = len(self.local_ranks)
+        try:
+            p = make_persist_plan(self.grid, self.filt, loops, k, self.sms // nloc, self.pbands, R,
+                                  peers=self.world > 1, warps=warps)
+        except ValueError:
+            return None
+        if p is None:
+            return None
+        # the device must really keep that many CTAs resident (registers / shared memory of the instance)
+        try:
+            d = self.drivers[self.local_ranks[0]]
+            cap = K.persist_capacity(d.persist_params(p, loops, 0, 0, 0, 0))
+        except K.CudaError:
+            return None
+        return p if p.nty * p.ntx * nloc <= cap else None
 
     def _plan_cache(self, mode: str) -> dict:
-        return {"stream": self._plans, "resident": self._rplans, "resident2": self._r2plans,
-                "resident3": self._r3plans}[mode]
+        return {"stream": self._plans, "resident": self._pplans}[mode]
 
     def plan_for(self, mode: str, loops: int) -> StreamPlan | None:
-        return self.plan(loops) if mode == "stream" else self.resident_plan(loops, self._VARIANT[mode])
+        return self.plan(loops) if mode == "stream" else self.resident_plan(loops)
 
     # -- on-device autotuning ----------------------------------------------------------------------
-    def autotune(self, loops: int, max_candidates: int = 14, reps: int = 2) -> dict:
-        """Measure candidate (mode, k, R) plans for ``loops`` iterations on this machine and keep the
-        fastest. The model-based planner is good at ranking but blind to box-specific effects
+    def autotune(self, loops: int, max_candidates: int = 16, reps: int = 2) -> dict:
+        """Measure candidate (mode, warps, k, R) plans for ``loops`` iterations on this machine and keep
+        the fastest. The model-based planner is good at ranking but blind to box-specific effects
         (launch gaps, cross-GPU skew); a few milliseconds of measurement settle it. Collective: every
-        rank times the same candidates in the same order and the decision uses the max over ranks,
-        so all ranks adopt the same plan. Overwrites the tile buffers with synthetic data — call it
-        before loading real input."""
+        rank times the same candidates in the same order, executes the same collectives whether or not
+        a candidate failed locally, and the decision uses the max over ranks — so all ranks adopt the
+        same plan. Overwrites the tile buffers with synthetic data: call it before loading real input."""
         if loops <= 0:
             return {}
         cands: list[tuple[str, StreamPlan]] = []
 
-        def add(mode: str, k: int, R: int) -> None:
+        def add(mode: str, k: int | None, R: int | None, warps: int = 16) -> None:
             try:
                 if mode == "stream":
                     p = make_plan(self.grid, self.filt, loops, k, self.sms, self.bands, R)
                 else:
-                    var = self._VARIANT[mode]
-                    p = make_resident_plan(self.grid, self.filt, loops, k, self.sms // len(self.local_ranks),
-                                           (self.bands, self.bands2, self.bands3)[var], R,
-                                           peers=self.world > 1, dual=max(var, 0))
+                    p = self._persist_candidate(loops, k, R, warps)
             except ValueError:
                 return
             if p is not None and (mode, p) not in cands:
                 cands.append((mode, p))
 
-        modes = [m for m in ("stream", "resident") if self.mode in ("auto", m)]
-        if self.bands2 and (self.mode == "resident2" or (self.mode == "auto" and AUTO_RESIDENT2)):
-            modes.append("resident2")
-        if self.bands3 and self.mode == "resident3":      # never picked automatically (not run on hardware yet)
-            modes.append("resident3")
+        modes = [m for m in MODES if self.mode in ("auto", m)]
         per_mode = max(4, max_candidates // max(1, len(modes)))
         for mode in modes:
-            base = self.plan_for(mode, loops)
-            if base is None:
-                continue
             mine = len(cands)
-            cands.append((mode, base))
-            bands = {"resident2": self.bands2, "resident3": self.bands3}.get(mode, self.bands)
-            for k in sorted({max(1, base.k - 2), max(1, base.k - 1), base.k + 1, base.k + 2, base.k + 5,
-                             max(1, base.k // 2), base.k * 2} - {base.k}):
-                if self.halo_depth or k > loops:
+            variants = (16,) if mode == "stream" else ((self.warps,) if self.warps else (8, 16))
+            bands = self.bands if mode == "stream" else self.pbands
+            for w in variants:
+                n0 = len(cands)
+                add(mode, self.halo_depth, self.band, w)
+                if len(cands) == n0:
                     continue
-                for R in ([base.R] + [b for b in bands if b != base.R]):
-                    if self.band and R != self.band:
+                base = cands[n0][1]
+                for k in sorted({max(1, base.k - 2), max(1, base.k - 1), base.k + 1, base.k + 2, base.k + 4,
+                                 max(1, base.k // 2), base.k * 2} - {base.k}):
+                    if self.halo_depth or k > loops:
                         continue
-                    add(mode, k, R)
+                    add(mode, k, self.band, w)          # the model's best band height for that depth
+                    if not self.band:
+                        add(mode, k, base.R, w)
             # rank this mode's candidates by the model and keep its most promising ones (the models of
-            # different kernels are not comparable with each other — the measurement decides that)
+            # the two kernels are not comparable with each other — the measurement decides that)
             own = sorted(cands[mine:], key=lambda mp: mp[1].est_us_per_launch *
                          (-(-loops // mp[1].k) if mp[0] == "stream" else 1))
             cands[mine:] = own[:per_mode]
-        saved = (self.mode, dict(self._plans), dict(self._rplans), dict(self._r2plans), dict(self._r3plans))
+        saved = (self.mode, dict(self._plans), dict(self._pplans), dict(self._tuned))
+        self._tuned.pop(loops, None)
         results = []
         for mode, p in cands:
             self.mode = mode
@@ -230,7 +240,9 @@ class FusedRuntime:
             best = None
             try:
                 self.prepare(loops)
-                self._barrier()
+                for d in self.drivers.values():
+                    d.reset_status()
+                K.stream_sync(self.stream)
                 for trial in range(reps + 1):           # trial 0 warms up
                     steps = 1 if trial == 0 else 4
                     e0, e1 = K.Event(), K.Event()
@@ -247,70 +259,70 @@ class FusedRuntime:
                     if trial:
                         ms = e0.elapsed_ms(e1) / steps
                         best = ms if best is None else min(best, ms)
-                self._barrier()
+                if any(d.read_status()[0] for d in self.drivers.values()):
+                    best = None                          # a watchdog fired: not a candidate
             except Exception:          # a candidate the kernels reject is simply not a candidate
                 best = None
-            if best is not None and self.world > 1:
+            # the same collectives on every rank, failed or not
+            self._barrier()
+            if self.world > 1:
                 import torch
-                t = torch.tensor([best], dtype=torch.float64, device="cuda")
+                t = torch.tensor([best if best is not None else float("inf")], dtype=torch.float64, device="cuda")
                 self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
                 best = float(t.item())
+                if best == float("inf"):
+                    best = None
             if best is not None:
                 results.append((best, mode, p))
-        self.mode, self._plans, self._rplans, self._r2plans, self._r3plans = saved
+        self.mode, self._plans, self._pplans, self._tuned = saved
         if not results:
             return {}
         results.sort(key=lambda r: r[0])
         ms, mode, p = results[0]
-        self._tuned = getattr(self, "_tuned", {})
         self._tuned[loops] = mode
         self._plan_cache(mode)[loops] = p
         return {"mode": mode, "plan": dict(p.__dict__), "ms": ms,
-                "tried": [(round(r[0], 4), r[1], r[2].k, r[2].R) for r in results]}
+                "tried": [(round(r[0], 4), r[1], r[2].W if r[1] != "stream" else 0, r[2].k, r[2].R) for r in results]}
 
     def choose_mode(self, loops: int) -> str:
-        tuned = getattr(self, "_tuned", {}).get(loops)
+        tuned = self._tuned.get(loops)
         if tuned and self.mode == "auto":
             return tuned
-        if self.mode in ("stream", "resident", "resident2", "resident3"):
+        if self.mode in MODES:
             if self.mode != "stream" and self.plan_for(self.mode, loops) is None:
-                raise ValueError(f"{self.mode} mode requested but the tile does not fit on chip")
+                raise ValueError("resident mode requested but the tile does not fit on chip "
+                                 "(or its geometry is not supported by the persistent kernel)")
             return self.mode
-        # "auto", from measurements on B200 (profiles/README.md): on 1-2 GPUs one in-kernel exchange
-        # costs about as much as a relaunch + reload, and streaming wins by 4-8 % (0.47 vs 0.51 ms on
-        # one GPU, 0.31 vs 0.32 ms on two); from 4 GPUs up the per-launch cross-GPU skew dominates and
-        # the persistent kernel wins (0.21 vs 0.26 ms on eight).
-        if self.world >= 4 and self.resident_plan(loops) is not None:
-            return "resident"
-        return "stream"
+        # "auto": the persistent kernel whenever the tile fits on chip — one launch, the image never
+        # leaves the registers, exchanges hidden behind a co-resident CTA (profiles/README.md)
+        return "resident" if self.resident_plan(loops) is not None else "stream"
 
-    def _enqueue_resident(self, loops: int, variant: int = 0) -> tuple[StreamPlan, int]:
-        plan = self.resident_plan(loops, variant)
+    def _enqueue_resident(self, loops: int) -> tuple[StreamPlan, int]:
+        plan = self.resident_plan(loops)
         nblocks = -(-loops // plan.k)
         first_wait, self._first_wait = getattr(self, "_first_wait", 0), 0
         signal = self.epoch + 1 if self.multi else 0
         bank1, self._first_bank1 = getattr(self, "_first_bank1", False), False
-        params = {r: self.drivers[r].resident_params(plan, loops, self.parity, first_wait if self.multi else 0,
-                                                     signal, self.cta_epoch, slot=self.slot,
-                                                     wait_bank1=bank1) for r in self.local_ranks}
-        for p in params.values():
-            p.dual = variant            # 0 single-phase, 1 split-phase, 2 split-phase + protocol warp
+        params = {r: self.drivers[r].persist_params(plan, loops, self.parity, first_wait if self.multi else 0,
+                                                    signal, self.cta_epoch, slot=self.slot,
+                                                    wait_bank1=bank1, peer_scope=self.world > 1)
+                  for r in self.local_ranks}
         if self._rank_streams:
             fork = K.Event().record(self.stream)
             joins = []
             for r, st in self._rank_streams.items():
                 K.stream_wait_event(st, fork)
-                K.resident_launch(params[r], st)
+                K.persist_launch(params[r], st)
                 joins.append(K.Event().record(st))
             for ev in joins:
                 K.stream_wait_event(self.stream, ev)
             self._keep = (fork, joins)
         else:
-            K.resident_launch(params[self.local_ranks[0]], self.stream)
+            K.persist_launch(params[self.local_ranks[0]], self.stream)
         if self.multi:
             self.epoch += 1
-        self.cta_epoch += nblocks
-        self.parity ^= nblocks & 1
+        self.cta_epoch += nblocks - 1     # contiguous epochs: the inbox parity keeps alternating
+        self.parity ^= 1                  # reads one buffer of the pair, writes the other
         return plan, len(self.local_ranks)
 
     def enqueue(self, loops: int) -> tuple[StreamPlan | None, int]:
@@ -319,7 +331,7 @@ class FusedRuntime:
             return None, 0
         mode = self.choose_mode(loops)
         if mode != "stream":
-            return self._enqueue_resident(loops, self._VARIANT[mode])
+            return self._enqueue_resident(loops)
         plan = self.plan(loops)
         ks = plan.launches(loops)
         n = len(self.local_ranks)
@@ -402,10 +414,12 @@ class FusedRuntime:
             return
         mode = self.choose_mode(loops)
         plan = self.plan_for(mode, loops)
-        resident = self._VARIANT[mode] + 1
-        key = (plan.R, resident)
+        key = (plan.R, plan.W if mode != "stream" else 0)
         if key not in getattr(self, "_prepared", set()):
-            K.kernel_prepare(self.filt.kind, self.grid.channels, plan.R, resident)
+            if mode == "stream":
+                K.kernel_prepare(self.filt.kind, self.grid.channels, plan.R)
+            else:
+                K.persist_capacity(self.drivers[self.local_ranks[0]].persist_params(plan, loops, 0, 0, 0, 0))
             self._prepared = getattr(self, "_prepared", set()) | {key}
 
     def run(self, loops: int, rep, sync: bool = True) -> None:

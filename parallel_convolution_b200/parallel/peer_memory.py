@@ -37,7 +37,7 @@ class PeerGroup:
     def exchange(self, mem: RankMemory, neighbors: list[int]) -> list[RankMemory | None]:
         """Export ``mem``, gather everybody's handles, map the neighbours. Collective."""
         mine = {"bufs": [K.ipc_export(p) for p in mem.bufs], "ctl": K.ipc_export(mem.flags),
-                "nbytes": mem.nbytes}
+                "arena": K.ipc_export(mem.arena), "nbytes": mem.nbytes}
         table: list[dict | None] = [None] * self.world
         self.dist.all_gather_object(table, mine)
         views: list[RankMemory | None] = []
@@ -52,8 +52,9 @@ class PeerGroup:
                     h = table[r]
                     bufs = [K.ipc_open(b) for b in h["bufs"]]
                     ctl = K.ipc_open(h["ctl"])
-                    self._opened += bufs + [ctl]
-                    cache[r] = RankMemory.view(bufs, ctl, h["nbytes"])
+                    arena = K.ipc_open(h["arena"])
+                    self._opened += bufs + [ctl, arena]
+                    cache[r] = RankMemory.view(bufs, ctl, h["nbytes"], arena)
                 views.append(cache[r])
         return views
 

@@ -23,11 +23,14 @@ def main():
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--band", type=int, default=0)
     ap.add_argument("--mode", default="stream")
+    ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--grid", default="")
     ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
     f = Filter.parse(a.filter)
-    g = TileGrid.create(a.height, a.width, a.channels, a.workers)
-    vc = VirtualCluster(g, f, halo_depth=a.k or None, band=a.band or None, mode=a.mode)
+    grid = tuple(int(v) for v in a.grid.split("x")) if a.grid else None
+    g = TileGrid.create(a.height, a.width, a.channels, a.workers, grid)
+    vc = VirtualCluster(g, f, halo_depth=a.k or None, band=a.band or None, mode=a.mode, warps=a.warps or None)
     vc.synth(1)
     plan = vc.rt.plan_for(vc.rt.choose_mode(a.loops), a.loops)
     vc.run(a.loops)

@@ -131,16 +131,17 @@ def test_reference_assets_have_the_documented_format():
 
 
 def test_native_planner_invariants():
-    from parallel_convolution_b200.parallel.plan import plan_resident, plan_stream
+    from parallel_convolution_b200.parallel.plan import plan_persist, plan_stream
     for rows, cb, C, kind, loops in [(2520, 5760, 3, 2, 100), (2520, 1920, 1, 2, 100), (630, 2880, 3, 1, 7),
                                      (16384, 16384, 1, 0, 500), (37, 41, 1, 2, 3)]:
         p = plan_stream(rows, cb, C, kind, loops)
         assert p.TH + 2 * p.k <= 16 * p.R and p.HB >= p.k * C and p.HB % 16 == 0
         assert p.TWB + 2 * p.HB == 512 and p.ntx * p.TWB >= cb and p.nty * p.TH >= rows
         assert sum(p.launches(loops)) == loops
-    r = plan_resident(2520, 5760, 3, 2, 100)
-    assert r is not None and r.ntx * r.nty <= 148 and r.TH >= r.k
-    assert plan_resident(16384, 16384, 1, 2, 100) is None      # does not fit on chip -> stream
+    for warps in (8, 16):
+        r = plan_persist(2520, 5760, 3, 2, 100, warps=warps)
+        assert r is not None and r.ntx * r.nty <= 148 * (16 // warps) and r.TH >= r.k and r.W == warps
+    assert plan_persist(16384, 16384, 1, 2, 100) is None      # does not fit on chip -> stream
 
 
 @pytest.mark.parametrize("name", ["gaussian", "box", "edge", "sharpen", "sobel_x"])

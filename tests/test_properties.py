@@ -6,7 +6,7 @@ from hypothesis import given, settings, strategies as st
 from parallel_convolution_b200.models.filters import Filter
 from parallel_convolution_b200.ops import host
 from parallel_convolution_b200.parallel.decomposition import TileGrid
-from parallel_convolution_b200.parallel.plan import plan_resident, plan_stream
+from parallel_convolution_b200.parallel.plan import plan_persist, plan_stream
 
 
 @settings(max_examples=60, deadline=None)
@@ -49,9 +49,10 @@ def test_stream_plans_are_always_launchable(rows, cb, c, kind, loops):
     assert p.HB % 16 == 0 and p.HB >= p.k * c and p.TWB + 2 * p.HB == 512
     assert p.ntx * p.TWB >= cb * c and p.nty * p.TH >= rows
     assert sum(p.launches(loops)) == loops and all(1 <= k <= p.k for k in p.launches(loops))
-    r = plan_resident(rows, cb * c, c, kind, loops)
-    if r is not None:
-        assert r.ntx * r.nty <= 148 and r.TH >= r.k and r.TWB >= r.HB
+    for warps in (8, 16):
+        r = plan_persist(rows, cb * c, c, kind, loops, warps=warps)
+        if r is not None:
+            assert r.W == warps and r.ntx * r.nty <= 148 * (16 // warps) and r.TH >= r.k and r.TWB >= r.HB
 
 
 @settings(max_examples=40, deadline=None)
@@ -77,31 +78,41 @@ def test_integer_filters_are_exact_in_fp32(w, s, seed):
 
 @settings(max_examples=150, deadline=None)
 @given(rows=st.integers(40, 4000), cb=st.integers(64, 12000), c=st.sampled_from([1, 3, 4]),
-       kind=st.sampled_from([0, 1, 2]), loops=st.integers(1, 120), sms=st.sampled_from([37, 74, 148]))
-def test_split_phase_plans_are_launchable(rows, cb, c, kind, loops, sms):
-    """Plans for the split-phase resident kernel: two virtual tile rows per CTA, everything co-resident."""
-    from parallel_convolution_b200.parallel.plan import plan_resident
+       kind=st.sampled_from([0, 1, 2]), loops=st.integers(1, 120), sms=st.sampled_from([16, 37, 74, 148]),
+       warps=st.sampled_from([8, 16]), nbr_rows=st.booleans(), nbr_cols=st.booleans())
+def test_persist_plans_are_launchable(rows, cb, c, kind, loops, sms, warps, nbr_rows, nbr_cols):
+    """Plans of the persistent kernel satisfy everything its launcher checks (persist_kernel.cu) and fit
+    the exchange arena layout (xplan.h)."""
+    from parallel_convolution_b200.parallel.fused import persist_arena_bytes
     cb = cb // c * c or c
-    p = plan_resident(rows, cb, c, kind, loops, sms=sms, dual=True)
+    p = plan_persist(rows, cb, c, kind, loops, sms=sms, warps=warps,
+                     min_nbr_rows=rows if nbr_rows else None, min_nbr_cols=cb // c if nbr_cols else None)
     if p is None:
         return
-    assert p.dual and p.nty % 2 == 0 and (p.nty // 2) * p.ntx <= sms
-    assert (p.nty + 2) * (p.ntx + 2) <= 1024
-    assert p.TH + 2 * p.k <= 16 * p.R and p.TH >= p.k
+    assert p.W == warps and p.nty * p.ntx <= sms * (16 // warps) and p.nty * p.ntx <= 1024
+    assert p.TH + 2 * p.k <= warps * p.R and p.TH >= p.k and 1 <= p.k <= loops
     assert p.HB % 16 == 0 and p.HB >= p.k * c and p.TWB + 2 * p.HB == 512 and p.TWB >= p.HB
-    assert p.nty * p.TH >= rows and p.ntx * p.TWB >= cb
+    assert p.nty * p.TH >= rows > (p.nty - 1) * p.TH and p.ntx * p.TWB >= cb > (p.ntx - 1) * p.TWB
+    if nbr_rows:
+        assert rows - (p.nty - 1) * p.TH >= p.k
+    if nbr_cols:
+        assert cb % 16 == 0 and cb - (p.ntx - 1) * p.TWB >= p.HB
+    assert persist_arena_bytes(p) > 0
 
 
-@settings(max_examples=60, deadline=None)
-@given(gr=st.integers(1, 3), gc=st.integers(1, 3), half_rows=st.integers(1, 5), ntx=st.integers(1, 4),
-       nblocks=st.integers(1, 5))
-def test_split_phase_flag_protocol_never_deadlocks(gr, gc, half_rows, ntx, nblocks):
-    """Replay of the split-phase resident kernel's wait/publish program (scripts/sim_split_phase.py mirrors
-    resident2_kernel.cuh): for any rank grid and CTA grid every CTA must run to completion."""
-    import importlib.util
-    import os
-    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "sim_split_phase.py")
-    spec = importlib.util.spec_from_file_location("sim_split_phase", path)
-    sim = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(sim)
-    assert sim.simulate(gr, gc, 2 * half_rows, ntx, nblocks) == []
+@settings(max_examples=25, deadline=None)
+@given(h=st.integers(20, 90), wpx=st.integers(40, 400), c=st.sampled_from([1, 3]), k=st.integers(1, 4),
+       R=st.sampled_from([2, 3, 4]), warps=st.sampled_from([8, 16]), loops=st.integers(1, 9),
+       seed=st.integers(0, 1000))
+def test_emulated_exchange_random_geometry(h, wpx, c, k, R, warps, loops, seed):
+    """Random single-rank geometries through the CPU replay of the persistent kernel's exchange."""
+    if warps * R - 2 * k < k:
+        return
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (h, wpx) if c == 1 else (h, wpx, c), dtype=np.uint8)
+    f = Filter.builtin("gaussian")
+    got = host.xplan_emulate(img, f.spec, loops, (1, 1), k, R, warps)
+    if isinstance(got, int):
+        assert got in (-2,)
+        return
+    assert np.array_equal(got, host.oracle(img, f.spec, loops))
