@@ -44,6 +44,26 @@ def main() -> int:
     exe = os.path.join(out, "cuda_conv")
     ok = proc.returncode == 0 and os.path.exists(exe)
     print("built" if ok else "FAILED", exe)
+    # Second bar: the same unmodified sources with the one flag the shipped Makefile lacks,
+    # -arch=sm_100a on its nvcc compile line (cuda/Makefile:11) — native Blackwell SASS instead of a JIT of
+    # the compute_52 PTX. The Makefile's three compile commands and its link command, replayed verbatim.
+    out2 = os.path.join(DST, "cuda_sm100a")
+    if os.path.isdir(out2):
+        writable(out2)
+        shutil.rmtree(out2)
+    shutil.copytree(src, out2)
+    writable(out2)
+    log2 = []
+    ok2 = True
+    for cmd in (["gcc", "-c", "main.c", "-O2"], ["gcc", "-c", "funcs.c", "-O2"],
+                ["nvcc", "-c", "cuda_convolute.cu", "-arch=sm_100a"],
+                ["nvcc", "-o", "cuda_conv", "main.o", "funcs.o", "cuda_convolute.o", "-O2"]):
+        p2 = subprocess.run(cmd, cwd=out2, env=env, capture_output=True, text=True)
+        log2.append(" ".join(cmd) + "\n" + p2.stdout + p2.stderr)
+        ok2 = ok2 and p2.returncode == 0
+    with open(os.path.join(DST, "build_sm100a.log"), "w") as f:
+        f.write("\n".join(log2))
+    print("built" if ok2 else "FAILED", os.path.join(out2, "cuda_conv"))
     return 0 if ok else 2
 
 

@@ -17,9 +17,17 @@ Two numbers are measured with the same engine API:
 * ``e2e``    — end to end through ``ConvEngine``: every step copies its input tiles from pinned host
   memory to the device, iterates, and reads the result tiles back to pinned host memory.
 
+After the timed regions one more step runs on a known synthetic image and its result is compared byte
+for byte with the native CPU engine (``"verified": true``; the run fails otherwise) — at every N.
+``whole_program`` is the wall clock of the stand-alone binary ``pconv_native image 1920 2520 100 rgb``
+(process start, CUDA context, file read, H2D, loop, D2H, file write): the like-for-like counterpart of
+the reference's own end-to-end number (its only timer wraps all of that, cuda/main.c:20,48-50).
+
 ``--impl reference`` runs the UNMODIFIED reference ``cuda_conv`` (built by its own Makefile into
-``baseline/_ref`` by ``baseline/build_reference.py``) on the same image shape through its own CLI.
-It exists only for N=1 — the reference has no multi-GPU program.
+``baseline/_ref`` by ``baseline/build_reference.py``) on the same image shape through its own CLI:
+W warm-up runs, K timed runs of 100 iterations. A second row reports the same sources compiled with
+``-arch=sm_100a``. It exists only for N=1 — the reference has no multi-GPU program
+(SURVEY.md §0).
 """
 from __future__ import annotations
 
@@ -41,6 +49,42 @@ WIDTH, HEIGHT, CHANNELS, LOOPS, FILTER = 1920, 2520, 3, 100, "gaussian"
 BASELINE_MPX_S = 537.6
 SLOTS = 3   # buffer sets of the pipelined end-to-end path: H2D(i+1) || iterate(i) || D2H(i-1)
 METRIC = "Mpixels/sec, 3x3 RGB conv 1920x2520, 100 iters (whole job, device-timed, max over ranks)"
+MODEL = "3x3 gaussian blur /16 (reference default filter), 1920x2520 RGB, 100 iterations"
+
+
+def shared_config(n_gpus: int, grid: str) -> dict:
+    """The part of ``config`` that is identical, key for key, in both arms."""
+    return {"model": MODEL, "image": f"{WIDTH}x{HEIGHT} RGB", "iterations_per_step": LOOPS,
+            "global_batch": 1, "seq_len": WIDTH * HEIGHT,
+            "parallelism": f"2-D block decomposition {grid} over {n_gpus} GPU(s)"}
+
+
+def make_image_file(path: str) -> None:
+    import numpy as np
+    if os.path.exists(path) and os.path.getsize(path) == WIDTH * HEIGHT * CHANNELS:
+        return
+    rng = np.random.default_rng(1)
+    rng.integers(0, 256, WIDTH * HEIGHT * CHANNELS, dtype=np.uint8).tofile(path)
+
+
+def whole_program(exe: str, work: str, img: str, runs: int, warm: int) -> dict:
+    """Wall clock of ``exe image 1920 2520 100 rgb`` (the reference's CLI grammar), best and median."""
+    import statistics
+    times = []
+    for i in range(warm + runs):
+        t0 = time.perf_counter()
+        out = subprocess.run([exe, os.path.basename(img), str(WIDTH), str(HEIGHT), str(LOOPS), "rgb"],
+                             cwd=work, capture_output=True, text=True, timeout=900)
+        dt = time.perf_counter() - t0
+        if out.returncode != 0:
+            raise RuntimeError(f"{exe} failed (rc={out.returncode}): {out.stderr[-300:]}")
+        if i >= warm:
+            times.append(dt)
+    best = min(times)
+    return {"seconds_best": round(best, 4), "seconds_median": round(statistics.median(times), 4), "runs": runs,
+            "value": round(WIDTH * HEIGHT * LOOPS / best / 1e6, 1), "unit": "Mpx/s",
+            "what": "wall clock of the whole program: process start + CUDA context + file read + H2D + "
+                    "100 iterations + D2H + file write"}
 
 
 def parse_args():
@@ -51,6 +95,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--backend", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--mode", default="auto")
+    ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--grid", default="", help="tile grid RxC (default: the reference's divide_rows choice)")
     ap.add_argument("--halo-depth", type=int, default=0)
     ap.add_argument("--filter", default=FILTER)
     ap.add_argument("--no-autotune", action="store_true", help="use the model-based plan as is")
@@ -89,9 +135,11 @@ def run_ours(a) -> dict | None:
     from parallel_convolution_b200.ops import cuda as K
     from parallel_convolution_b200.utils.clocks import ClockSampler
 
+    grid = tuple(int(v) for v in a.grid.lower().split("x")) if a.grid else None
     eng = ConvEngine(width=WIDTH, height=HEIGHT, channels=CHANNELS, filter=a.filter,
                      backend=a.backend, mode=a.mode, halo_depth=a.halo_depth or None, device=local,
-                     slots=SLOTS if a.backend == "fused" else 1)
+                     slots=SLOTS if a.backend == "fused" else 1, grid=grid,
+                     **({"warps": a.warps} if a.warps else {}))
     tuned = {}
     if not a.no_autotune and a.backend == "fused":
         try:
@@ -169,6 +217,19 @@ def run_ours(a) -> dict | None:
     kmode = impl.choose_mode(LOOPS) if hasattr(impl, "choose_mode") else "stream"
     plan = impl.plan_for(kmode, LOOPS) if hasattr(impl, "plan_for") else impl.plan(LOOPS)
     h2d = allsum(tile_bytes)
+
+    # ---- correctness of what was timed: one more step on a known image vs the native CPU engine -------
+    from parallel_convolution_b200.ops import host as HOST
+    eng.load_synthetic(seed=4242)
+    vrep = eng.iterate(LOOPS)                  # same engine, same plan, same kernels as the timed steps
+    got = eng.gather()
+    verified, mismatches = True, 0
+    if rank == 0:
+        ref_in = HOST.synth_rect(4242, WIDTH * CHANNELS, 0, HEIGHT, 0, WIDTH * CHANNELS).reshape(HEIGHT, WIDTH, CHANNELS)
+        want = HOST.cpu_run_image(ref_in, eng.filter.spec, LOOPS)
+        mismatches = int((got.reshape(want.shape) != want).sum())
+        verified = mismatches == 0
+    probe = dict(vrep.probe) if vrep.probe else {}
     eng.close()
     if dist:
         dist.barrier()
@@ -179,8 +240,37 @@ def run_ours(a) -> dict | None:
     from parallel_convolution_b200.utils import roofline
     kk = int(getattr(plan, "k", 1) or 1) if plan else 1
     roof = roofline.terms(WIDTH, HEIGHT, CHANNELS, LOOPS, a.gpus, kk, eng.filter.kind_name,
-                          g.halo_bytes_per_iteration(0, kk))
+                          g.halo_bytes_per_iteration(0, kk), sm_clock_hz=(clocks.get("sm_mhz") or 0) * 1e6)
     roof_frac = roofline.fraction(ms / K_steps * 1e-3, roof)
+    # where the time goes, per N: how much of the arithmetic is useful (the rest is halo recompute) and
+    # what one in-kernel exchange cost the probe CTA (persistent kernel: wait = signal + flags + fetch)
+    useful = None
+    if plan:
+        RH = getattr(plan, "RH", 16 * plan.R)
+        useful = round(WIDTH * HEIGHT * CHANNELS / a.gpus / (plan.ntx * plan.nty * RH * 512.0), 4)
+    nx = max(int(probe.get("exchanges", 0)), 1)
+    exchange = ({"exchanges_per_step": int(probe.get("exchanges", 0)),
+                 "push_us": round(probe.get("publish_us", 0.0) / nx, 3),
+                 "signal_wait_fetch_us": round(probe.get("wait_us", 0.0) / nx, 3),
+                 "inbox_to_registers_us": round(probe.get("reload_us", 0.0) / nx, 3),
+                 "compute_us_total": round(probe.get("compute_us", 0.0), 1),
+                 "note": "in-kernel %globaltimer probe of one interior CTA during the verification step"}
+                if probe.get("exchanges") else None)
+    whole = None
+    if a.gpus == 1 and a.backend == "fused":
+        try:
+            from parallel_convolution_b200 import build as B
+            work = "/tmp/pconv_ref_bench"
+            os.makedirs(work, exist_ok=True)
+            img = os.path.join(work, "synthetic_1920_2520.raw")
+            make_image_file(img)
+            whole = whole_program(str(B.NATIVE_BIN), work, img, runs=max(3, min(K_steps, 10)), warm=2)
+        except Exception as e:  # noqa: BLE001
+            whole = {"unavailable": str(e)[:200]}
+    if not verified:
+        print(json.dumps({"impl": "ours", "error": f"verification failed: {mismatches} bytes differ from the CPU engine",
+                          "n_gpus": a.gpus}), flush=True)
+        raise SystemExit(3)
     return {
         "metric": METRIC, "value": round(value, 1), "unit": "Mpx/s", "n_gpus": a.gpus,
         "steps": K_steps, "warmup": W, "ms_per_step": round(ms / K_steps, 5),
@@ -188,16 +278,17 @@ def run_ours(a) -> dict | None:
         "vs_baseline": round(value / BASELINE_MPX_S, 2),
         "dtype": "uint8 storage, integer arithmetic bit-identical to the reference's fp32 accumulate",
         "data": "synthetic random-pixel images of the benchmark shape (device generator)",
-        "impl": "ours",
-        "config": {"model": "3x3 gaussian blur /16 (reference default filter)", "image": f"{WIDTH}x{HEIGHT} RGB",
-                   "iterations_per_step": LOOPS, "global_batch": 1, "seq_len": WIDTH * HEIGHT,
-                   "parallelism": f"2-D block decomposition {g.grid_rows}x{g.grid_cols} over {a.gpus} GPU(s)",
+        "impl": "ours", "verified": True,
+        "verification": "one extra step (synthetic image, 100 iterations, same engine and plan) compared byte for "
+                        "byte with the native CPU engine: 0 mismatches",
+        "config": {**shared_config(a.gpus, f"{g.grid_rows}x{g.grid_cols}"),
                    "backend": a.backend, "kernel_mode": kmode,
                    "autotune": {"tried": tuned.get("tried", [])[:8]} if tuned else "off", "plan": dict(plan.__dict__) if plan else {},
                    "cache": f"inputs rotate through a device pool of {pool} images/GPU "
                             f"({pool * tile_bytes >> 20} MiB > L2 {l2 >> 20} MiB); no L2 flush needed",
                    "timed_region": "pool->tile device copy + halo protocol + all iterations of every step",
                    "roofline_s_per_step": roof, "fraction_of_binding_roofline": round(roof_frac, 4),
+                   "useful_arithmetic_fraction": useful, "exchange_probe": exchange,
                    "baseline_mpx_s": BASELINE_MPX_S,
                    "baseline_source": "BASELINE.md: MPI+OMP rgb 1920x2520, 16 processes (best published RGB rate)"},
         "clocks": clocks,
@@ -207,6 +298,7 @@ def run_ours(a) -> dict | None:
                         "iterates 100x, copies the result device -> pinned host; 3 buffer slots / 3 streams overlap "
                         "the copies of neighbouring steps with the iterations (all K steps inside the timed region)"},
         "gpu_launches": launches,
+        "whole_program": whole,
     }
 
 
@@ -217,59 +309,86 @@ def run_reference(a) -> dict:
                 "the reference has no multi-GPU program (its CUDA variant is single-device; its MPI "
                 "variants are CPU-only and no MPI toolchain exists in this image)"}
     exe = os.path.join(ROOT, "baseline", "_ref", "cuda", "cuda_conv")
-    if not os.path.exists(exe):
+    exe100 = os.path.join(ROOT, "baseline", "_ref", "cuda_sm100a", "cuda_conv")
+    if not os.path.exists(exe) or not os.path.exists(exe100):
         try:
             subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "build_reference.py")],
                            check=True, capture_output=True, timeout=600)
         except Exception as e:  # noqa: BLE001
-            return {"impl": "reference", "unavailable": f"reference cuda_conv could not be built: {e}"}
+            if not os.path.exists(exe):
+                return {"impl": "reference", "unavailable": f"reference cuda_conv could not be built: {e}"}
     if not os.path.exists(exe):
         return {"impl": "reference", "unavailable": "baseline/_ref/cuda/cuda_conv missing after build"}
-    import numpy as np
     work = "/tmp/pconv_ref_bench"
     os.makedirs(work, exist_ok=True)
     img = os.path.join(work, "synthetic_1920_2520.raw")
-    rng = np.random.default_rng(1)
-    rng.integers(0, 256, WIDTH * HEIGHT * CHANNELS, dtype=np.uint8).tofile(img)
+    make_image_file(img)
 
-    def once(loops: int) -> float:
+    def once(binary: str, loops: int) -> tuple[float, float]:
+        """(the reference's own timer, wall clock of the process) for one run."""
         t0 = time.perf_counter()
-        out = subprocess.run([exe, os.path.basename(img), str(WIDTH), str(HEIGHT), str(loops), "rgb"],
+        out = subprocess.run([binary, os.path.basename(img), str(WIDTH), str(HEIGHT), str(loops), "rgb"],
                              cwd=work, capture_output=True, text=True, timeout=900)
         wall = time.perf_counter() - t0
         for line in out.stdout.splitlines():
             if "Execution time" in line:
-                return float(line.split(":")[1].split()[0])   # the reference's own timer
+                return float(line.split(":")[1].split()[0]), wall
         raise RuntimeError(f"reference printed no time (rc={out.returncode}, wall={wall:.1f}s): {out.stderr[-300:]}")
 
-    try:
-        for _ in range(max(1, min(a.warmup, 2))):
-            once(LOOPS)                        # JIT of the compute_52 PTX + page-in
-        reps = max(2, min(a.steps, 4))
+    def measure(binary: str, K: int, W: int) -> dict:
+        import statistics
+        for _ in range(W):
+            once(binary, LOOPS)                   # JIT of the compute_52 PTX + page-in
+        runs = [once(binary, LOOPS) for _ in range(K)]        # the K timed steps: 100 iterations each
+        t100 = min(r[0] for r in runs)
+        wall100 = min(r[1] for r in runs)
         long_loops = LOOPS + 1000                 # a long run isolates the per-iteration cost from the
-        t100 = min(once(LOOPS) for _ in range(reps))          # ~1.3 s of start-up, file I/O and JIT
-        tlong = min(once(long_loops) for _ in range(reps))
+        tlong = min(once(binary, long_loops)[0] for _ in range(2))   # ~1.3 s of start-up, file I/O and JIT
+        marginal_s = max((tlong - t100) / (long_loops - LOOPS), 1e-9)   # per-iteration device cost only
+        return {"t100": t100, "t100_median": statistics.median(r[0] for r in runs), "wall100": wall100,
+                "tlong": tlong, "marginal_s": marginal_s}
+
+    K_steps, W = max(1, a.steps), max(a.warmup, 1)
+    try:
+        m = measure(exe, K_steps, W)
     except Exception as e:  # noqa: BLE001
         return {"impl": "reference", "unavailable": f"reference cuda_conv failed to run: {e}"}
     px = WIDTH * HEIGHT
-    marginal_s = max((tlong - t100) / (long_loops - LOOPS), 1e-9)   # per-iteration device cost only
-    value = px / marginal_s / 1e6
-    whole = px * LOOPS / t100 / 1e6
-    return {"metric": METRIC, "value": round(value, 1), "unit": "Mpx/s", "n_gpus": 1, "steps": reps,
-            "warmup": max(1, min(a.warmup, 2)), "ms_per_step": round(marginal_s * LOOPS * 1e3, 4),
+    value = px / m["marginal_s"] / 1e6
+    whole = px * LOOPS / m["t100"] / 1e6
+    row100 = None
+    if os.path.exists(exe100):
+        try:
+            m2 = measure(exe100, max(2, min(K_steps, 5)), 1)
+            row100 = {"binary": "baseline/_ref/cuda_sm100a/cuda_conv (same unmodified sources, nvcc -arch=sm_100a)",
+                      "value": round(px / m2["marginal_s"] / 1e6, 1), "unit": "Mpx/s",
+                      "ms_per_step": round(m2["marginal_s"] * LOOPS * 1e3, 4),
+                      "e2e_value": round(px * LOOPS / m2["t100"] / 1e6, 1), "seconds_100_iters": m2["t100"]}
+        except Exception as e:  # noqa: BLE001
+            row100 = {"unavailable": str(e)[:200]}
+    return {"metric": METRIC, "value": round(value, 1), "unit": "Mpx/s", "n_gpus": 1, "steps": K_steps,
+            "warmup": W, "ms_per_step": round(m["marginal_s"] * LOOPS * 1e3, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_MPX_S, 3),
             "dtype": "uint8 storage, FP64 per-tap arithmetic (cuda/cuda_convolute.cu:38-40)",
             "data": "synthetic random-pixel image of the benchmark shape (raw file in /tmp)",
             "impl": "reference",
-            "config": {"model": "3x3 gaussian blur /16", "image": f"{WIDTH}x{HEIGHT} RGB",
-                       "iterations_per_step": LOOPS, "binary": "baseline/_ref/cuda/cuda_conv (unmodified sources, "
+            "config": {**shared_config(1, "1x1"),
+                       "binary": "baseline/_ref/cuda/cuda_conv (unmodified sources, "
                        "its own Makefile: sm_52 SASS + compute_52 PTX, JIT on B200)",
-                       "timing": "value = marginal loop rate from the reference's own host timer "
-                                 "((t(1100 it) - t(100 it)) / 1000, best of N runs each); e2e = its "
-                                 "whole-program time for 100 iterations incl. file I/O"},
-            "e2e": {"value": round(whole, 1), "unit": "Mpx/s", "seconds_100_iters": t100,
-                    "seconds_1100_iters": tlong},
-            "gpu_launches": LOOPS}
+                       "timing": f"{W} warm-up runs, {K_steps} timed runs of 100 iterations; value = marginal loop "
+                                 "rate from the reference's own host timer ((t(1100 it) - t(100 it)) / 1000, best "
+                                 "run each); e2e / whole_program = its whole-program time for 100 iterations incl. "
+                                 "file I/O, H2D, D2H (its timer covers exactly that, cuda/main.c:20,48-50)",
+                       "rebuilt_sm_100a": row100},
+            "e2e": {"value": round(whole, 1), "unit": "Mpx/s", "seconds_100_iters": m["t100"],
+                    "seconds_100_iters_median": m["t100_median"], "seconds_1100_iters": m["tlong"],
+                    "h2d_bytes_per_step": WIDTH * HEIGHT * CHANNELS, "d2h_bytes_per_step": WIDTH * HEIGHT * CHANNELS,
+                    "note": "pageable cudaMemcpy inside gpuConvolute (cuda/cuda_convolute.cu:60,94-96), plus file I/O"},
+            "whole_program": {"seconds_best": round(m["wall100"], 4), "value": round(px * LOOPS / m["wall100"] / 1e6, 1),
+                              "unit": "Mpx/s", "runs": K_steps,
+                              "what": "wall clock of the whole program: process start + CUDA context + PTX JIT + "
+                                      "file read + H2D + 100 iterations + D2H + file write"},
+            "gpu_launches": LOOPS * K_steps}
 
 
 def main() -> int:

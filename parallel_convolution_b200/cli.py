@@ -181,7 +181,7 @@ def main(argv: list[str] | None = None) -> int:
             state = ckpt.load_state(out_path) if a.resume else None
             if state is not None:
                 ckpt.check_compatible(state, a.width, a.height, channels, eng.filter, a.loops)
-                eng.load_file(ckpt.image_path(out_path))
+                eng.load_file(ckpt.image_path(out_path, state))
                 done = state["iterations_done"]
             elif a.synthetic is not None:
                 eng.load_synthetic(a.synthetic)

@@ -102,6 +102,8 @@ typedef struct pconv_persist_params {
     uint32_t epoch_base;     // exchange b (1-based) carries epoch_base + b; the host advances it by
                              // ceil(loops/k) - 1 per run (epochs stay contiguous: the inbox parity alternates)
     uint32_t peer_scope;     // 1: neighbouring ranks are other GPUs (system-scope flags)
+    uint32_t debug_skip;     // timing experiments only (wrong results): 1 no push, 2 no wait/fetch, 4 no refresh
+    uint32_t pad_;
     pconv_sync_t sync;       // launch-level protocol, identical to the stream kernel's
 } pconv_persist_params_t;
 int pconv_persist_launch(const pconv_persist_params_t* p, void* stream);

@@ -30,7 +30,7 @@ static PersistFn pick_kernel(int kind, int C, int R, int W) {
 
 static size_t smem_bytes(int W, const XGeom& x) {
     const size_t head = W == 8 ? offsetof(PersistSmem<8>, inbox) : offsetof(PersistSmem<16>, inbox);
-    return head + (size_t)x.slot_chunks * 16;
+    return head + (size_t)x.slot_chunks * 16 + (size_t)2 * x.k * 32 * 16;   // + outbox
 }
 
 // Geometry checks shared by the launcher and pconv_persist_arena_bytes; fills *x.
@@ -130,6 +130,7 @@ extern "C" int pconv_persist_launch(const pconv_persist_params_t* p, void* strea
     a.loops = p->loops;
     a.epoch_base = p->epoch_base;
     a.peer_scope = p->peer_scope;
+    a.debug_skip = p->debug_skip;
     a.sync = p->sync;
     if (a.sync.timeout_ns == 0) a.sync.timeout_ns = 10ull * 1000 * 1000 * 1000;
 

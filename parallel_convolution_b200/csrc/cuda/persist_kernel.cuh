@@ -51,6 +51,8 @@ struct PersistArgs {
     int loops;
     uint32_t epoch_base;    // exchange b (1-based) carries epoch epoch_base + b
     uint32_t peer_scope;    // 1: neighbouring ranks are other GPUs (system-scope release / acquire)
+    uint32_t debug_skip;    // timing experiments only (results are WRONG): 1 no push stores, 2 no flag wait /
+                            // fetch, 4 no inbox->register refresh
     pconv_sync_t sync;
 };
 
@@ -98,7 +100,7 @@ struct PersistSmem {
     alignas(8) uint64_t mbar;
     unsigned long long wait_ns;
     uint32_t dead;                 // a watchdog fired in this CTA: stop waiting, run through (status[0] is set)
-    alignas(128) uint4 inbox[1];   // slot_chunks entries (dynamic)
+    alignas(128) uint4 inbox[1];   // slot_chunks entries (dynamic), followed by the outbox: 2 x k x 32 chunks
 };
 
 template <int KIND, int C, int R, int W>
@@ -177,15 +179,40 @@ persist_kernel(const __grid_constant__ PersistArgs A) {
 #pragma unroll
     for (int i = 0; i < R; ++i)
         if (grw + i >= 0 && grw + i < g.img_rows) rowmask |= 1u << i;
-    const bool masked = need_cols || gr0 < 0 || gr0 + RH > g.img_rows;
 
-    // Row / lane classes of this thread's band (common/xplan.h), fixed for the whole run.
-    const XThread xt = xp_thread(x, vr, vc, rr0, lane, R);
+    // ---- per-thread exchange plan (common/xplan.h), fixed for the whole run -------------------------
+    // Horizontal borders / halos (every warp, every interior row): straight between registers and the
+    // neighbour's slot / my inbox. Vertical borders (k rows held by one or two warps): the border warps dump
+    // those rows into a shared-memory outbox and ALL warps push them, one (direction, row) pair per warp at a
+    // time — otherwise the border warps' eight-direction epilogue is what the whole CTA waits for.
     const uint32_t nbr_mask = S.t.nbr_mask, remote_mask = S.t.remote_mask;
+    const XThread xt0 = xp_thread(x, vr, vc, rr0, lane, R);
+    const uint32_t m_int = xt0.m_int;                      // band rows inside the interior
+    const uint32_t m_up = xt0.m_up, m_dn = xt0.m_dn;       // band rows of the top / bottom interior border
+    const bool has_halo_rows = (xt0.m_top | xt0.m_bot) != 0u;   // warp-uniform
+    int hz_fetch_idx = -1, hz_push_D = -1, hz_push_idx = 0;
+    const bool narrow = vc < 2 * nh;     // CTA-uniform: a lane may sit in BOTH side borders -> two passes
+    {
+        uint32_t m;
+        int idx0, stride, src;
+        if (xp_fetch(x, xt0, 1, vr, vc, rr0, lane, &src, &m, &idx0, &stride) && ((nbr_mask >> src) & 1u) && m)
+            hz_fetch_idx = idx0;
+#pragma unroll
+        for (int D = 3; D <= 5; D += 2)     // one side border per lane: W and E leave in the SAME instructions
+            if (((nbr_mask >> D) & 1u) && xp_push(x, xt0, D, vr, vc, rr0, lane, &m, &idx0, &stride)) {
+                hz_push_D = D; hz_push_idx = idx0;
+            }
+    }
+    uint4* const outbox = &S.inbox[x.slot_chunks];         // [2][k][32]: rows pushed up, rows pushed down
+    constexpr uint32_t kAllRows = (1u << R) - 1u;
 
-    const bool probe = A.sync.status != nullptr && threadIdx.x == 0 &&
-                       blockIdx.x == (unsigned)((x.nty / 2) * x.ntx + x.ntx / 2);
-    uint64_t t_pub = 0, t_wait = 0, t_load = 0, t_comp = 0, t_mark = probe ? globaltimer_ns() : 0;
+    // Phase probe: thread 0 of EVERY CTA accumulates where its time goes; one interior CTA adds its
+    // numbers to status[4..], and each CTA leaves (push, wait, compute) in words 10..15 of its own flag
+    // line (read back by scripts/cta_profile.py to find the CTAs that pace the grid).
+    const bool probe = A.sync.status != nullptr && threadIdx.x == 0;
+    const bool probe_main = probe && blockIdx.x == (unsigned)((x.nty / 2) * x.ntx + x.ntx / 2);
+    uint64_t t_pub = 0, t_wait = 0, t_load = 0, t_comp = 0, t_sig = 0, t_poll = 0, t_mark = probe ? globaltimer_ns() : 0;
+    uint64_t t_hz = 0, t_b1 = 0, t_v = 0;   // finer split of t_pub (development probe)
     auto lap = [&](uint64_t& acc) {
         if (probe) { const uint64_t t = globaltimer_ns(); acc += t - t_mark; t_mark = t; }
     };
@@ -197,22 +224,62 @@ persist_kernel(const __grid_constant__ PersistArgs A) {
             const uint32_t epoch = A.epoch_base + (uint32_t)b;
             const int par = (int)(epoch & 1u);
             // ---- 1. push my border chunks into the neighbours' inboxes ------------------------------
+            if (!(A.debug_skip & 1u)) {
+                // horizontal: W and E (the LSU cost is per instruction, not per active lane: one pass)
+                if (!narrow) {
+                    if (hz_push_D >= 0 && !(A.debug_skip & 8u)) {
+                        uint4* p = reinterpret_cast<uint4*>(S.t.dst_slot[par][hz_push_D]) + hz_push_idx;
+                        if (m_int == kAllRows) {
 #pragma unroll
-            for (int D = 0; D < 9; ++D) {
-                if (D == 4 || !((nbr_mask >> D) & 1u)) continue;
-                uint32_t m;
-                int idx0, stride;
-                if (xp_push(x, xt, D, vr, vc, rr0, lane, &m, &idx0, &stride)) {
-                    uint4* base = reinterpret_cast<uint4*>(S.t.dst_slot[par][D]) + idx0;
+                            for (int i = 0; i < R; ++i) st_weak(p + i * nh, rows[i]);
+                        } else {
 #pragma unroll
-                    for (int i = 0; i < R; ++i)
-                        if ((m >> i) & 1u) __stcg(base + i * stride, rows[i]);
+                            for (int i = 0; i < R; ++i)
+                                if ((m_int >> i) & 1u) st_weak(p + i * nh, rows[i]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int D = 3; D <= 5; D += 2) {
+                        uint32_t m;
+                        int idx0, stride;
+                        if (((nbr_mask >> D) & 1u) && xp_push(x, xt0, D, vr, vc, rr0, lane, &m, &idx0, &stride)) {
+                            uint4* p = reinterpret_cast<uint4*>(S.t.dst_slot[par][D]) + idx0;
+#pragma unroll
+                            for (int i = 0; i < R; ++i)
+                                if ((m >> i) & 1u) st_weak(p + i * stride, rows[i]);
+                        }
+                    }
+                }
+                lap(t_hz);
+                // vertical, step 1: border rows -> outbox (warp-uniform row tests)
+                if ((m_up | m_dn) && !(A.debug_skip & 16u)) {
+#pragma unroll
+                    for (int i = 0; i < R; ++i) {
+                        if ((m_up >> i) & 1u) outbox[(rr0 + i - k) * 32 + lane] = rows[i];
+                        if ((m_dn >> i) & 1u) outbox[(k + rr0 + i - vr) * 32 + lane] = rows[i];
+                    }
                 }
             }
             __syncthreads();
+            lap(t_b1);
+            // vertical, step 2: every warp pushes (direction, row) pairs from the outbox
+            if (!(A.debug_skip & 17u)) {
+                for (int pr = warp; pr < 6 * k; pr += W) {
+                    const int dsel = pr / k, r = pr - dsel * k;
+                    const int D = dsel < 3 ? dsel : dsel + 3;          // 0 1 2 | 6 7 8
+                    if (!((nbr_mask >> D) & 1u)) continue;
+                    const XBlock sb = xp_send(x, D, vr, vc);
+                    if (lane < sb.width)
+                        st_weak(reinterpret_cast<uint4*>(S.t.dst_slot[par][D]) + x.off[8 - D] + r * sb.width + lane,
+                                outbox[((D > 4 ? k : 0) + r) * 32 + sb.chunk0 + lane]);
+                }
+            }
+            lap(t_v);
+            __syncthreads();
             lap(t_pub);
             // ---- 2./3. signal the consumers, arm my inbox, fetch each block as its flag arrives -------
-            if (warp == 0) {
+            if (warp == 0 && !(A.debug_skip & 2u)) {
                 const bool mine = lane < 9 && ((nbr_mask >> lane) & 1u);
                 const bool far = A.peer_scope && ((remote_mask >> lane) & 1u);
                 // (the release store alone publishes the pushed chunks: the CTA's stores happen-before
@@ -223,6 +290,7 @@ persist_kernel(const __grid_constant__ PersistArgs A) {
                 }
                 if (lane == 0) mbar_arrive_expect_tx(&S.mbar, S.t.total_bytes);
                 __syncwarp();
+                lap(t_sig);
                 if (mine) {
                     const uint32_t* fl = S.t.my_flags + lane;
                     uint64_t ns = 0;
@@ -235,9 +303,10 @@ persist_kernel(const __grid_constant__ PersistArgs A) {
                     bulk_g2s(&S.inbox[x.off[lane]], S.t.my_slot[par] + (size_t)x.off[lane] * 16,
                              S.t.blk_bytes[lane], &S.mbar);
                 }
+                lap(t_poll);
             }
             // ---- 4. wait for the inbox, refresh my halo from shared memory ---------------------------
-            if (!mbar_try_wait(&S.mbar, phase)) {
+            if (!(A.debug_skip & 2u) && !mbar_try_wait(&S.mbar, phase)) {
                 const uint64_t t0 = globaltimer_ns();
                 while (!mbar_try_wait(&S.mbar, phase)) {
                     if (globaltimer_ns() - t0 > 2 * A.sync.timeout_ns) {   // (the pollers time out first)
@@ -246,39 +315,65 @@ persist_kernel(const __grid_constant__ PersistArgs A) {
                     }
                 }
             }
-            phase ^= 1u;
+            if (!(A.debug_skip & 2u)) phase ^= 1u;
             lap(t_wait);
+            if (!(A.debug_skip & 4u)) {
+                if (hz_fetch_idx >= 0) {           // left / right halo lanes: interior rows
+                    const uint4* p = &S.inbox[hz_fetch_idx];
+                    if (m_int == kAllRows) {
 #pragma unroll
-            for (int grp = 0; grp < 3; ++grp) {
-                uint32_t m;
-                int src, idx0, stride;
-                if (xp_fetch(x, xt, grp, vr, vc, rr0, lane, &src, &m, &idx0, &stride) && ((nbr_mask >> src) & 1u)) {
-                    const uint4* p = &S.inbox[idx0];
+                        for (int i = 0; i < R; ++i) rows[i] = p[i * nh];
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < R; ++i)
-                        if ((m >> i) & 1u) rows[i] = p[i * stride];
+                        for (int i = 0; i < R; ++i)
+                            if ((m_int >> i) & 1u) rows[i] = p[i * nh];
+                    }
+                }
+                if (has_halo_rows) {               // the warps holding top / bottom halo rows
+#pragma unroll
+                    for (int grp = 0; grp < 3; grp += 2) {
+                        uint32_t m;
+                        int src, idx0, stride;
+                        if (xp_fetch(x, xt0, grp, vr, vc, rr0, lane, &src, &m, &idx0, &stride) && ((nbr_mask >> src) & 1u)) {
+                            const uint4* p = &S.inbox[idx0];
+#pragma unroll
+                            for (int i = 0; i < R; ++i)
+                                if ((m >> i) & 1u) rows[i] = p[i * stride];
+                        }
+                    }
                 }
             }
             lap(t_load);
         }
         // ---- 5. iterate ---------------------------------------------------------------------------
         const int kb = min(k, A.loops - b * k);
-        if (masked) region_iterate<KIND, C, R, true, W>(rows, S.eb, kb, cmask, rowmask, need_cols, A.f);
-        else region_iterate<KIND, C, R, false, W>(rows, S.eb, kb, cmask, rowmask, need_cols, A.f);
+        region_iterate<KIND, C, R, W>(rows, S.eb, kb, cmask, rowmask, need_cols, A.f);
         __syncthreads();  // edge buffers: the next block restarts at parity 0; inbox reads are done
         lap(t_comp);
     }
     if (probe) {
+        unsigned long long* mine = reinterpret_cast<unsigned long long*>(
+            reinterpret_cast<uint32_t*>(A.arena[4]) + xp_flag_word((int)blockIdx.x, 10));
+        mine[0] = t_pub + t_hz + t_b1 + t_v;
+        mine[1] = t_sig + t_poll + t_wait;
+        mine[2] = t_comp;
+    }
+    if (probe_main) {
         unsigned long long* st = reinterpret_cast<unsigned long long*>(A.sync.status);
-        atomicAdd(st + 4, (unsigned long long)t_pub);
-        atomicAdd(st + 5, (unsigned long long)t_wait);
+        atomicAdd(st + 4, (unsigned long long)(t_pub + t_hz + t_b1 + t_v));
+        atomicAdd(st + 11, (unsigned long long)t_hz);
+        atomicAdd(st + 12, (unsigned long long)t_b1);
+        atomicAdd(st + 13, (unsigned long long)t_v);
+        atomicAdd(st + 5, (unsigned long long)(t_sig + t_poll + t_wait));
         atomicAdd(st + 6, (unsigned long long)t_load);
         atomicAdd(st + 7, (unsigned long long)t_comp);
         atomicAdd(st + 8, (unsigned long long)(nblocks - 1));
+        atomicAdd(st + 9, (unsigned long long)t_sig);     // of [5]: release stores + arming the mbarrier
+        atomicAdd(st + 10, (unsigned long long)t_poll);   // of [5]: polling my own flag word + issuing its bulk copy
     }
 
     // ---- final interior -> my output tile -----------------------------------------------------------
-    store_band<R>(rows, xt.hcls == 1 ? xt.m_int : 0u, A.dst, g, grw, gb);
+    store_band<R>(rows, (lane >= nh && lane < nh + vc) ? m_int : 0u, A.dst, g, grw, gb);
     if (threadIdx.x == 0 && S.wait_ns) record_wait(A.sync.status, S.wait_ns);
 
     // ---- launch-level protocol: publish "run done" -------------------------------------------------

@@ -78,11 +78,9 @@ stream_kernel(const __grid_constant__ StreamArgs A) {
 #pragma unroll
         for (int i = 0; i < R; ++i)
             if (grw + i >= 0 && grw + i < g.img_rows) rowmask |= 1u << i;
-        const bool masked = need_cols || gr0 < 0 || gr0 + RH > g.img_rows;  // CTA-uniform
 
         // ---- k fused iterations in registers ------------------------------------------------------
-        if (masked) region_iterate<KIND, C, R, true>(rows, eb, k, cmask, rowmask, need_cols, A.f);
-        else region_iterate<KIND, C, R, false>(rows, eb, k, cmask, rowmask, need_cols, A.f);
+        region_iterate<KIND, C, R>(rows, eb, k, cmask, rowmask, need_cols, A.f);
 
         // ---- store the interior straight from registers ------------------------------------------
         const bool col_in = (16 * lane >= A.HB) && (16 * lane < A.HB + A.TWB);

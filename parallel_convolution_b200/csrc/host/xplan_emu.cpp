@@ -128,25 +128,47 @@ extern "C" int pconv_xplan_emulate(const uint8_t* img, uint8_t* out, int64_t H, 
             for (int r = 0; r < nranks; ++r)
                 for (int c = 0; c < ncta; ++c) {
                     const int ti = c / x.ntx, tj = c % x.ntx, vr = xp_vr(x, ti), vc = xp_vc(x, tj);
+                    // vertical step 1 (device: border warps dump their rows into the shared-memory outbox)
+                    std::vector<uint8_t> outbox((size_t)2 * k * 512, 0xAB);
+                    for (int w = 0; w < W; ++w)
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const XThread t = xp_thread(x, vr, vc, w * R, lane, R);
+                            for (int i = 0; i < R; ++i) {
+                                const uint8_t* src = &ctas[r][c].reg[(size_t)(w * R + i) * 512 + 16 * lane];
+                                if ((t.m_up >> i) & 1u) std::memcpy(&outbox[((size_t)(w * R + i - k) * 32 + lane) * 16], src, 16);
+                                if ((t.m_dn >> i) & 1u) std::memcpy(&outbox[((size_t)(k + w * R + i - vr) * 32 + lane) * 16], src, 16);
+                            }
+                        }
                     for (int D = 0; D < 9; ++D) {
                         if (D == 4) continue;
                         const XPeer p = xp_peer(x, ti, tj, D);
                         const int dst_rank = p.rank_dir == 4 ? r : rank_in_dir(r, p.rank_dir);
                         if (dst_rank < 0) continue;
                         uint8_t* slot = arena[dst_rank].data() + xp_slot_byte(x, p.cta, par);
-                        for (int w = 0; w < W; ++w)
-                            for (int lane = 0; lane < 32; ++lane) {
-                                const XThread t = xp_thread(x, vr, vc, w * R, lane, R);
-                                uint32_t m;
-                                int idx0, stride;
-                                if (!xp_push(x, t, D, vr, vc, w * R, lane, &m, &idx0, &stride)) continue;
-                                for (int i = 0; i < R; ++i)
-                                    if ((m >> i) & 1u) {
-                                        const int idx = idx0 + i * stride;
-                                        if (idx < 0 || idx >= x.slot_chunks) return -10;   // out of the slot
-                                        std::memcpy(slot + (size_t)idx * 16, &ctas[r][c].reg[(size_t)(w * R + i) * 512 + 16 * lane], 16);
-                                    }
-                            }
+                        if (D == 3 || D == 5) {      // horizontal: straight from the "registers", per thread
+                            for (int w = 0; w < W; ++w)
+                                for (int lane = 0; lane < 32; ++lane) {
+                                    const XThread t = xp_thread(x, vr, vc, w * R, lane, R);
+                                    uint32_t m;
+                                    int idx0, stride;
+                                    if (!xp_push(x, t, D, vr, vc, w * R, lane, &m, &idx0, &stride)) continue;
+                                    for (int i = 0; i < R; ++i)
+                                        if ((m >> i) & 1u) {
+                                            const int idx = idx0 + i * stride;
+                                            if (idx < 0 || idx >= x.slot_chunks) return -10;   // out of the slot
+                                            std::memcpy(slot + (size_t)idx * 16, &ctas[r][c].reg[(size_t)(w * R + i) * 512 + 16 * lane], 16);
+                                        }
+                                }
+                        } else {                     // vertical step 2: (direction, row) pairs from the outbox
+                            const XBlock sb = xp_send(x, D, vr, vc);
+                            for (int rr = 0; rr < k; ++rr)
+                                for (int lane = 0; lane < sb.width; ++lane) {
+                                    const int idx = x.off[8 - D] + rr * sb.width + lane;
+                                    if (idx < 0 || idx >= x.slot_chunks || sb.chunk0 + lane >= 32) return -10;
+                                    std::memcpy(slot + (size_t)idx * 16,
+                                                &outbox[((size_t)((D > 4 ? k : 0) + rr) * 32 + sb.chunk0 + lane) * 16], 16);
+                                }
+                        }
                     }
                 }
             // FETCH: bulk copies of the existing sources' blocks, then per-thread halo refresh

@@ -83,6 +83,8 @@ int main(int argc, char** argv) {
     }
 
     const double t_all = now_s();
+    const bool timing = std::getenv("PCONV_NATIVE_TIMING") != nullptr;   // phase times on stderr
+    auto mark = [&](const char* what) { if (timing) std::fprintf(stderr, "[pconv_native] %-14s %.4f s\n", what, now_s() - t_all); };
     const int64_t rb = W * C, nbytes = rb * H;
     if (pconv_file_size(image.c_str()) < nbytes) {
         std::fprintf(stderr, "pconv_native: %s is shorter than %lld bytes\n", image.c_str(), (long long)nbytes);
@@ -100,6 +102,7 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "pconv_native: cannot read %s\n", image.c_str());
         return EXIT_FAILURE;
     }
+    mark("file read");
     double loop_s = 0.0;
     if (cpu || pconv_cuda_device_count() == 0) {
         const double t0 = now_s();
@@ -107,6 +110,7 @@ int main(int argc, char** argv) {
         loop_s = now_s() - t0;
     } else {
         CK(pconv_cuda_set_device(0));
+        mark("cuda init");
         pconv_plan_request_t q{};
         q.tile_rows = H; q.tile_cb = rb; q.C = C; q.kind = f.kind; q.loops = loops > 0 ? loops : 1;
         q.sms = pconv_cuda_sm_count();
@@ -160,6 +164,7 @@ int main(int argc, char** argv) {
         }
         if (!pwarps) CK(pconv_kernel_prepare(f.kind, C, plan.R));   // one-time module load stays out of the loop time
         CK(pconv_cuda_stream_sync(stream));               // ... and so does the H2D copy (as in the reference's MPI timer)
+        mark("alloc+h2d+load");
         CK(pconv_cuda_event_record(e0, stream));
         if (pwarps) CK(pconv_persist_launch(&ps, stream));
         else if (!ks.empty()) CK(pconv_stream_run(pp, 1, ks.data(), (int)ks.size(), 0, 0, 0, nullptr, stream));
@@ -170,6 +175,7 @@ int main(int argc, char** argv) {
         float ms = 0.f;
         CK(pconv_cuda_event_elapsed_ms(e0, e1, &ms));
         loop_s = ms / 1e3;
+        mark("loop+d2h");
         pconv_cuda_free(bufA); pconv_cuda_free(bufB);
         if (arena) pconv_cuda_free(arena);
     }
@@ -178,6 +184,7 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "pconv_native: cannot write %s\n", out.c_str());
         return EXIT_FAILURE;
     }
+    mark("file write");
     std::printf("Execution time: %.3f sec\n", now_s() - t_all);
     std::printf("%f\n", loop_s);
     return EXIT_SUCCESS;

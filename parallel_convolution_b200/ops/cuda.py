@@ -60,7 +60,8 @@ class PersistParams(C.Structure):
                 ("loops", C.c_int32), ("k", C.c_int32), ("TH", C.c_int32), ("TWB", C.c_int32),
                 ("HB", C.c_int32), ("R", C.c_int32), ("W", C.c_int32), ("nty", C.c_int32),
                 ("ntx", C.c_int32), ("arena", C.c_void_p * 9), ("arena_bytes", C.c_int64),
-                ("epoch_base", C.c_uint32), ("peer_scope", C.c_uint32), ("sync", Sync)]
+                ("epoch_base", C.c_uint32), ("peer_scope", C.c_uint32), ("debug_skip", C.c_uint32),
+                ("pad_", C.c_uint32), ("sync", Sync)]
 
 
 class CudaError(RuntimeError):

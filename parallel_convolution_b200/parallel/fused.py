@@ -31,8 +31,8 @@ import os
 
 FLAG_BYTES = 256      # bank 0 (+0): launch epochs, bank 1 (+64): "input ready" step counters
 BANK1 = 64
-STATUS_WORDS = 9      # u64: error, max wait ns, sum wait ns, waits; persistent-kernel probe CTA: push /
-                      # signal+wait / inbox->register / compute ns, exchanges
+STATUS_WORDS = 14     # u64: error, max wait ns, sum wait ns, waits; persistent-kernel probe CTA: push /
+                      # signal+wait+fetch / inbox->register / compute ns, exchanges, of which signal / own poll
 # control block layout (one cudaMalloc, one IPC handle): flags | counter | status
 OFF_COUNTER, OFF_STATUS = FLAG_BYTES, FLAG_BYTES + 64
 CTL_BYTES = OFF_STATUS + 128
@@ -171,6 +171,7 @@ class TileDriver:
         p.nty, p.ntx = plan.nty, plan.ntx
         p.epoch_base = cta_epoch & 0xFFFFFFFF
         p.peer_scope = 1 if peer_scope else 0
+        p.debug_skip = int(os.environ.get("PCONV_PERSIST_SKIP", "0"))   # timing experiments only
         p.sync.local_flags = self.mem.flags + (BANK1 if wait_bank1 else 0)
         p.sync.done_counter = self.mem.counter
         p.sync.status = self.mem.status
@@ -224,7 +225,9 @@ class TileDriver:
         K.stream_sync(self.stream)
         self.probe = {"publish_us": float(out[4]) / 1e3, "wait_us": float(out[5]) / 1e3,
                       "reload_us": float(out[6]) / 1e3, "compute_us": float(out[7]) / 1e3,
-                      "exchanges": int(out[8])}
+                      "exchanges": int(out[8]), "signal_us": float(out[9]) / 1e3, "poll_us": float(out[10]) / 1e3,
+                      "push_hz_us": float(out[11]) / 1e3, "push_bar1_us": float(out[12]) / 1e3,
+                      "push_vert_us": float(out[13]) / 1e3}
         return bool(out[0]), float(out[1]) / 1e3, float(out[2]) / 1e3, int(out[3])
 
 

@@ -27,16 +27,18 @@ def measured_hbm_gbs() -> tuple[float, str]:
 
 
 def terms(width: int, height: int, channels: int, loops: int, gpus: int, k: int, path: str,
-          halo_bytes_per_exchange: int, sms: int = 148) -> dict:
-    """Seconds each resource needs at its peak for the whole run (per GPU)."""
+          halo_bytes_per_exchange: int, sms: int = 148, sm_clock_hz: float = 0.0) -> dict:
+    """Seconds each resource needs at its peak for the whole run (per GPU). ``sm_clock_hz``: the SM
+    clock sampled during the run (0: the nominal 1.9 GHz)."""
     hbm, src = measured_hbm_gbs()
+    clock = sm_clock_hz if sm_clock_hz > 1e8 else SM_CLOCK_HZ
     img = width * height * channels
     k = max(k, 1)
     return {
         "hbm_s": 2.0 * img / k * loops / gpus / (hbm * 1e9),
         "hbm_peak": f"{hbm:.0f} GB/s ({src})",
         "nvlink_halo_s": halo_bytes_per_exchange * (loops / k) / (NVLINK_GBS * 1e9),
-        "int_issue_s": img * loops / gpus / (ALU_BYTES_PER_CLK[path] * sms * SM_CLOCK_HZ),
+        "int_issue_s": img * loops / gpus / (ALU_BYTES_PER_CLK[path] * sms * clock),
         "int_issue_note": "modelled bound, not a measured peak",
     }
 

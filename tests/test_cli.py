@@ -78,6 +78,37 @@ def test_checkpoint_and_resume_are_bit_identical(raw, tmp_path):
     assert not os.path.exists(str(part) + ".ckpt.json")    # cleaned up after a complete run
 
 
+def test_checkpoint_is_crash_safe_after_the_first_one(raw, tmp_path):
+    """The second checkpoint goes to a new file; the sidecar always names a complete image whose size and
+    CRC are recorded — a truncated / corrupted state image is refused instead of silently resumed."""
+    p, img = raw
+    part = tmp_path / "part.raw"
+    r = run_cli(p, 56, 40, 10, "grey", "--backend", "cpu", "-o", part, "--checkpoint-every", 4, "--no-output")
+    assert r.returncode == 0, r.stderr
+    side = json.loads(open(str(part) + ".ckpt.json").read())
+    state_img = tmp_path / side["image"]
+    assert side["iterations_done"] == 8 and side["image"].endswith(".ckpt.8.raw")
+    assert side["bytes"] == 56 * 40 and os.path.getsize(state_img) == 56 * 40
+    assert not os.path.exists(str(part) + ".ckpt.4.raw")          # the previous image went away last
+    # a crash while the NEXT checkpoint image is being written leaves this pair intact: simulate the
+    # half-written newer file and make sure the resume still uses the complete one
+    (tmp_path / "part.raw.ckpt.12.raw").write_bytes(b"\x00" * 100)
+    full = tmp_path / "full.raw"
+    assert run_cli(p, 56, 40, 10, "grey", "--backend", "cpu", "-o", full).returncode == 0
+    r = run_cli(p, 56, 40, 10, "grey", "--backend", "cpu", "-o", part, "--resume")
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.fromfile(part, dtype=np.uint8), np.fromfile(full, dtype=np.uint8))
+    # a state image that does not match its sidecar (bit rot / interrupted overwrite) is refused
+    r = run_cli(p, 56, 40, 10, "grey", "--backend", "cpu", "-o", part, "--checkpoint-every", 4, "--no-output")
+    assert r.returncode == 0, r.stderr
+    side = json.loads(open(str(part) + ".ckpt.json").read())
+    data = bytearray((tmp_path / side["image"]).read_bytes())
+    data[7] ^= 0xFF
+    (tmp_path / side["image"]).write_bytes(bytes(data))
+    r = run_cli(p, 56, 40, 10, "grey", "--backend", "cpu", "-o", part, "--resume")
+    assert r.returncode != 0 and "checksum" in (r.stderr + r.stdout)
+
+
 def test_batch_mode_cpu(tmp_path):
     rng = np.random.default_rng(2)
     paths = []
