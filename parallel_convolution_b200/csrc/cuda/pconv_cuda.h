@@ -158,6 +158,15 @@ int pconv_cuda_pack_rect(const uint8_t* tile, int64_t pitch, int64_t row0, int64
 int pconv_cuda_unpack_rect(uint8_t* tile, int64_t pitch, int64_t row0, int64_t byte0,
                            int64_t rows, int64_t nbytes, const uint8_t* dense, void* stream);
 
+// The same for up to 8 rectangles in ONE launch (128-bit copies when pitch, width and both pointers are
+// 16-byte aligned): pack != 0 copies tile -> dense, else dense -> tile.
+typedef struct pconv_rect {
+    uint8_t* tile;
+    int64_t pitch, row0, byte0, rows, nbytes;
+    uint8_t* dense;
+} pconv_rect_t;
+int pconv_cuda_rect_batch(const pconv_rect_t* rects, int n, int pack, void* stream);
+
 // Number of kernels this library has launched since load (bench.py reports it as gpu_launches).
 int64_t pconv_cuda_launch_count(void);
 

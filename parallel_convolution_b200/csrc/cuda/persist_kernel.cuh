@@ -263,31 +263,36 @@ persist_kernel(const __grid_constant__ PersistArgs A) {
             }
             __syncthreads();
             lap(t_b1);
-            // vertical, step 2: every warp pushes (direction, row) pairs from the outbox
+            // vertical, step 2: all warps push the outbox rows, row r of every direction by warp r mod W
             if (!(A.debug_skip & 17u)) {
-                for (int pr = warp; pr < 6 * k; pr += W) {
-                    const int dsel = pr / k, r = pr - dsel * k;
+#pragma unroll
+                for (int dsel = 0; dsel < 6; ++dsel) {
                     const int D = dsel < 3 ? dsel : dsel + 3;          // 0 1 2 | 6 7 8
                     if (!((nbr_mask >> D) & 1u)) continue;
                     const XBlock sb = xp_send(x, D, vr, vc);
-                    if (lane < sb.width)
-                        st_weak(reinterpret_cast<uint4*>(S.t.dst_slot[par][D]) + x.off[8 - D] + r * sb.width + lane,
-                                outbox[((D > 4 ? k : 0) + r) * 32 + sb.chunk0 + lane]);
+                    if (lane < sb.width) {
+                        uint4* dst = reinterpret_cast<uint4*>(S.t.dst_slot[par][D]) + x.off[8 - D] + lane;
+                        const uint4* src = outbox + (D > 4 ? k : 0) * 32 + sb.chunk0 + lane;
+                        for (int r = warp; r < k; r += W) st_weak(dst + r * sb.width, src[r * 32]);
+                    }
                 }
             }
             lap(t_v);
             __syncthreads();
             lap(t_pub);
             // ---- 2./3. signal the consumers, arm my inbox, fetch each block as its flag arrives -------
+            // Warp 0 signals the neighbours on THIS GPU (gpu-scope release), arms the inbox and polls; warp 1
+            // signals the neighbours on other GPUs: a system-scope release waits for the NVLink writes to be
+            // acknowledged (a few us) and must not sit in front of the local signalling and polling.
+            if (warp == 1 && A.peer_scope && !(A.debug_skip & 2u)) {
+                if (lane < 9 && ((nbr_mask & remote_mask) >> lane) & 1u) st_release_sys(S.t.dst_flag[lane], epoch);
+            }
             if (warp == 0 && !(A.debug_skip & 2u)) {
                 const bool mine = lane < 9 && ((nbr_mask >> lane) & 1u);
                 const bool far = A.peer_scope && ((remote_mask >> lane) & 1u);
                 // (the release store alone publishes the pushed chunks: the CTA's stores happen-before
                 //  it through the barrier above — causality order is cumulative)
-                if (mine) {
-                    if (far) st_release_sys(S.t.dst_flag[lane], epoch);
-                    else st_release_gpu(S.t.dst_flag[lane], epoch);
-                }
+                if (mine && !far) st_release_gpu(S.t.dst_flag[lane], epoch);
                 if (lane == 0) mbar_arrive_expect_tx(&S.mbar, S.t.total_bytes);
                 __syncwarp();
                 lap(t_sig);

@@ -21,14 +21,16 @@ constexpr int kRegionBytes = 512, kWarps = 16;
 // Modelled SM throughput in region bytes per clock (B200 measurements, profiles/): only used to
 // rank candidate plans, never reported as a result.
 double bytes_per_clk(int kind) {
-    return kind == PCONV_KIND_SEP121 ? 20.0 : (kind == PCONV_KIND_INT ? 9.0 : 4.0);
+    return kind == PCONV_KIND_SEP121 ? 23.0 : (kind == PCONV_KIND_INT ? 9.0 : 4.0);
 }
-constexpr double kClockGHz = 1.9, kLaunchUs = 4.0, kLoadBytesPerUsPerSm = 40e3;
-// Persistent kernel (persist_kernel.cuh): what one exchange costs a CTA when nothing hides it (push +
-// release + flag round trip + bulk fetch), and what is left of it when a second CTA shares the SM and
-// computes meanwhile. Measured on B200 (profiles/README.md); only used to rank plans — the autotuner
-// measures the best few.
-constexpr double kExchangeUs = 1.6, kExchangeUsPeer = 4.5, kExchangeUsHidden = 0.35, kExchangeUsHiddenPeer = 1.5;
+constexpr double kClockGHz = 1.9, kLaunchUs = 6.0, kLoadBytesPerUsPerSm = 40e3;
+// Persistent kernel (persist_kernel.cuh): what one exchange costs a CTA — push (~2.3 us: the LSU cost is
+// per store instruction), release + flag round trip + bulk fetch (~2.6 us of which ~1.2 us is waiting for
+// the slowest neighbour), inbox -> registers (~1 us). A pushed exchange costs about the same across NVLink
+// (posted stores, local polling). Two CTAs sharing an SM do NOT hide each other's exchanges — every CTA of
+// the grid is ready at the same moment — they roughly halve the per-CTA cost instead. Measured on B200
+// (profiles/README.md); only used to rank plans — the autotuner measures the best few.
+constexpr double kExchangeUs = 6.3, kExchangeUsPeer = 7.5, kExchangeUsHidden = 3.7, kExchangeUsHiddenPeer = 4.5;
 
 int roundup(int v, int m) { return (v + m - 1) / m * m; }
 int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -82,8 +84,10 @@ extern "C" int pconv_plan(const pconv_plan_request_t* q, pconv_plan_t* out) {
                 const double on_sm = (double)ceil_div(ntx * nty, sms);       // CTAs sharing the busiest SM
                 const double t_x = on_sm > 1.0 ? (q->peers ? kExchangeUsHiddenPeer : kExchangeUsHidden)
                                                : (q->peers ? kExchangeUsPeer : kExchangeUs);
+                // a lone 8-warp CTA cannot fill the SM's issue slots (measured: ~15 % slower than 16 warps)
+                const double r_eff = (warps == 8 && on_sm == 1.0) ? 0.85 * rate : rate;
                 total = kLaunchUs + on_sm * (RH * (double)kRegionBytes + (double)TH * TWB) / kLoadBytesPerUsPerSm +
-                        (double)loops * on_sm * (RH * (double)kRegionBytes / rate) + (nblocks - 1) * on_sm * t_x;
+                        (double)loops * on_sm * (RH * (double)kRegionBytes / r_eff) + (nblocks - 1) * on_sm * t_x;
                 per_launch = total;
             } else {
                 const double t_tile = RH * (double)kRegionBytes / kLoadBytesPerUsPerSm +

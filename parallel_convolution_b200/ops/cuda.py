@@ -64,6 +64,11 @@ class PersistParams(C.Structure):
                 ("pad_", C.c_uint32), ("sync", Sync)]
 
 
+class Rect(C.Structure):
+    _fields_ = [("tile", C.c_void_p), ("pitch", C.c_int64), ("row0", C.c_int64), ("byte0", C.c_int64),
+                ("rows", C.c_int64), ("nbytes", C.c_int64), ("dense", C.c_void_p)]
+
+
 class CudaError(RuntimeError):
     pass
 
@@ -112,6 +117,7 @@ def lib() -> C.CDLL:
     L.pconv_cuda_flush_l2.argtypes = [vp, i64, vp]
     L.pconv_cuda_pack_rect.argtypes = [vp, i64, i64, i64, i64, i64, vp, vp]
     L.pconv_cuda_unpack_rect.argtypes = [vp, i64, i64, i64, i64, i64, vp, vp]
+    L.pconv_cuda_rect_batch.argtypes = [C.POINTER(Rect), C.c_int, C.c_int, vp]
     L.pconv_cuda_launch_count.restype = i64
     return L
 
@@ -290,6 +296,11 @@ def unpack_rect(tile: int, pitch: int, row0: int, byte0: int, rows: int, nbytes:
                 stream: int) -> None:
     _check(lib().pconv_cuda_unpack_rect(tile, pitch, row0, byte0, rows, nbytes, dense, stream),
            "unpack_rect")
+
+
+def rect_batch(rects, n: int, pack: bool, stream: int) -> None:
+    """``rects``: ctypes array of ``Rect``; one launch copies all of them (pack: tile -> dense)."""
+    _check(lib().pconv_cuda_rect_batch(rects, n, 1 if pack else 0, stream), "rect_batch")
 
 
 def kernel_prepare(kind: int, channels: int, band: int) -> None:

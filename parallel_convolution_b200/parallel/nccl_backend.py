@@ -4,10 +4,16 @@
 (BASELINE.json) — this is that baseline, kept honest so the fused backend has something real to
 beat. It is the GPU analogue of the reference's MPI schedule (``mpi/mpi_conv.c:164-248``):
 
-    every k iterations:  8 pack kernels (border strips -> dense send buffers)
-                         one grouped batch of isend/irecv over NCCL (torch.distributed)
-                         8 unpack kernels (dense receive buffers -> ghost strips)
+    every k iterations:  ONE pack kernel (all border strips -> dense send buffers, 128-bit copies)
+                         ONE ncclGroup of send/recv pairs (torch.distributed.batch_isend_irecv)
+                         ONE unpack kernel (dense receive buffers -> ghost strips)
                          one stream_kernel launch of k fused iterations
+
+and the whole run (every exchange and launch of ``loops`` iterations) is captured once into a CUDA graph
+and replayed, so no Python or launch latency sits between the steps — a tuned send/recv implementation,
+not a strawman. The graph replay is opt-in (``PCONV_NCCL_GRAPH=1``, used by ``bench/halo_sweep.py``):
+captured NCCL groups need every rank to capture and replay in lockstep, which a library default must not
+assume of its callers.
 
 The stencil kernel is the same sm_100a kernel as the fused backend; the only difference is where
 the halo comes from: instead of peer-mapped neighbour tiles, its eight neighbour "sources" are
@@ -44,6 +50,8 @@ class NcclRuntime:
         self.pitch = tile_pitch(grid)
         self.tstream = torch.cuda.current_stream()
         self.stream = int(self.tstream.cuda_stream)
+        self.use_graph = os.environ.get("PCONV_NCCL_GRAPH", "0") not in ("", "0")
+        self._graphs: dict = {}
         self.sms = K.sm_count()
         self.bands = K.band_heights(filt.kind)
         self.local_ranks = [rank] if world > 1 else [0]
@@ -142,44 +150,56 @@ class NcclRuntime:
                 s_cb = my_cb - s_c0
             else:
                 s_c0, s_cb = 0, my_cb
-            send = torch.empty(s_rows * s_cb, dtype=torch.uint8, device=dev)
+            send = torch.empty(max(s_rows * s_cb, 16), dtype=torch.uint8, device=dev)[:s_rows * s_cb]
             self.links.append({"d": d, "rank": r, "ghost": ghost, "gp": gp, "vbase": vbase,
                                "recv": recv, "fill": (fill_r0 - g_row0, fill_c0 - g_c0, fill_rows, fill_cb),
                                "send": send, "strip": (s_r0, s_c0, s_rows, s_cb)})
         self._ghost_key = key
+        self._graphs = {}
+        # descriptor batches of the fused pack / unpack kernels (the pack side per source parity)
+        n = len(self.links)
+        self._packs = []
+        for par in range(2):
+            arr = (K.Rect * max(n, 1))()
+            for i, L in enumerate(self.links):
+                r0, c0, nr, ncb = L["strip"]
+                arr[i] = K.Rect(self.mems[self.me].bufs[par], self.pitch, r0, c0, nr, ncb, L["send"].data_ptr())
+            self._packs.append(arr)
+        self._unpack = (K.Rect * max(n, 1))()
+        for i, L in enumerate(self.links):
+            r0, c0, nr, ncb = L["fill"]
+            self._unpack[i] = K.Rect(L["ghost"].data_ptr(), L["gp"], r0, c0, nr, ncb, L["recv"].data_ptr())
+        self._ops = []
+        for L in self.links:
+            self._ops.append(self.dist.P2POp(self.dist.isend, L["send"], L["rank"]))
+            self._ops.append(self.dist.P2POp(self.dist.irecv, L["recv"], L["rank"]))
+        if self._ops:     # connect the send/recv channels now (lazy in NCCL): a CUDA graph capture cannot
+            for req in self.dist.batch_isend_irecv(self._ops):
+                req.wait()
+            torch.cuda.synchronize()
+
+    def _cur_stream(self) -> int:
+        return int(self.torch.cuda.current_stream().cuda_stream)
 
     def _exchange(self, src_parity: int) -> int:
         """One halo exchange of the current state; returns kernels launched."""
-        dist, launched = self.dist, 0
-        tile_ptr = self.mems[self.me].bufs[src_parity]
-        ops = []
+        st = self._cur_stream()
+        n = len(self.links)
         if self.poison:
             for L in self.links:
                 L["ghost"].fill_(0xA5)
-        for L in self.links:
-            r0, c0, nr, ncb = L["strip"]
-            K.pack_rect(tile_ptr, self.pitch, r0, c0, nr, ncb, L["send"].data_ptr(), self.stream)
-            launched += 1
-            ops.append(dist.P2POp(dist.isend, L["send"], L["rank"]))
-            ops.append(dist.P2POp(dist.irecv, L["recv"], L["rank"]))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
+        if n:
+            K.rect_batch(self._packs[src_parity], n, True, st)
+            for req in self.dist.batch_isend_irecv(self._ops):     # one ncclGroup
                 req.wait()            # stream-ordered wait (NCCL): the next kernels see the data
-        for L in self.links:
-            r0, c0, nr, ncb = L["fill"]
-            K.unpack_rect(L["ghost"].data_ptr(), L["gp"], r0, c0, nr, ncb, L["recv"].data_ptr(), self.stream)
-            launched += 1
+            K.rect_batch(self._unpack, n, False, st)
         self.exchanges += 1
-        return launched
+        return 2 if n else 0
 
     # -- compute --------------------------------------------------------------------------------------
-    def enqueue(self, loops: int) -> tuple[StreamPlan | None, int]:
-        if loops <= 0:
-            return None, 0
-        plan = self.plan(loops)
+    def _enqueue_eager(self, plan: StreamPlan, loops: int) -> int:
         launched = 0
-        if self.world > 1:
-            self._build_ghosts(plan)
+        st = self._cur_stream()
         for k in plan.launches(loops):
             if self.world > 1:
                 launched += self._exchange(self.parity)
@@ -188,15 +208,46 @@ class NcclRuntime:
                 for L in self.links:
                     p.src[L["d"]] = L["vbase"]
                     p.src_pitch[L["d"]] = L["gp"]
-            K.stream_launch(p, self.stream)
+            K.stream_launch(p, st)
             launched += 1
             self.parity ^= 1
+        return launched
+
+    def enqueue(self, loops: int) -> tuple[StreamPlan | None, int]:
+        if loops <= 0:
+            return None, 0
+        plan = self.plan(loops)
+        if self.world > 1:
+            self._build_ghosts(plan)
+        if not (self.use_graph and self.world > 1 and not self.poison):
+            return plan, self._enqueue_eager(plan, loops)
+        # Whole run as ONE CUDA graph (captured per (loops, starting parity); NCCL send/recv groups are
+        # capturable): replaying it costs one launch from the host.
+        key = (loops, self.parity)
+        if key not in self._graphs:
+            torch = self.torch
+            p0, x0 = self.parity, self.exchanges
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    launched = self._enqueue_eager(plan, loops)
+                self._graphs[key] = (g, launched, self.parity, self.exchanges - x0)
+            except Exception:                       # capture not possible here: stay eager
+                self.use_graph = False
+                self.parity, self.exchanges = p0, x0
+                torch.cuda.synchronize()
+                return plan, self._enqueue_eager(plan, loops)
+            self.parity, self.exchanges = p0, x0    # capturing did not execute anything
+        g, launched, parity_after, nx = self._graphs[key]
+        g.replay()
+        self.parity = parity_after
+        self.exchanges += nx
         return plan, launched
 
     def run(self, loops: int, rep, sync: bool = True) -> None:
         torch = self.torch
         if loops > 0:
-            K.kernel_prepare(self.filt.kind, self.grid.channels, self.plan(loops).R, False)
+            K.kernel_prepare(self.filt.kind, self.grid.channels, self.plan(loops).R)
         if self.world > 1:
             torch.cuda.synchronize()
             self.dist.barrier()

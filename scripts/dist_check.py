@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--mode", default="auto")
     ap.add_argument("--grid", default="")
+    ap.add_argument("--warps", type=int, default=0)
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -42,7 +43,8 @@ def main():
     ref = host.cpu_run_image(img, f.spec, a.loops) if rank == 0 else None
     grid = tuple(int(v) for v in a.grid.split("x")) if a.grid else None
     eng = ConvEngine(width=a.width, height=a.height, channels=a.channels, filter=f, backend=a.backend,
-                     halo_depth=a.halo_depth or None, mode=a.mode, grid=grid)
+                     halo_depth=a.halo_depth or None, mode=a.mode, grid=grid,
+                     **({"warps": a.warps} if a.warps else {}))
     ok = True
     for rep in range(a.reps):     # twice: exercises epoch continuity / buffer reuse across runs
         eng.load_synthetic(42)
@@ -54,6 +56,7 @@ def main():
             print(f"[dist_check] rep={rep} backend={a.backend} world={dist.get_world_size()} "
                   f"grid={eng.grid.grid_rows}x{eng.grid.grid_cols} filter={f.name} loops={a.loops} "
                   f"elapsed_ms={r.elapsed_ms:.3f} max_wait_us={r.max_wait_us:.1f} waits={r.waits} "
+                  f"mode={eng._impl.choose_mode(a.loops) if hasattr(eng._impl, 'choose_mode') else '-'} "
                   f"plan={r.plan} probe={r.probe} {'OK' if same else 'MISMATCH ' + str(int((out.reshape(ref.shape) != ref).sum()))}",
                   flush=True)
     eng.close()
