@@ -1,6 +1,9 @@
 #!/usr/bin/env python
-"""Halo-exchange sweep (BASELINE.json config 5): square tiles of edge 256..16384 px on N GPUs,
-one exchange per iteration (k=1), fused peer-memory halo vs the NCCL send/recv baseline.
+"""Halo-exchange sweep (BASELINE.json config 5): square tiles of edge 256..16384 px on N GPUs, one
+exchange per iteration (k=1) or the planner's depth (--halo-depth 0): the fused backend (persistent kernel
+with pushed halos where the tile fits on chip, streaming kernel with pulled halos otherwise) vs the NCCL
+send/recv baseline (one pack kernel + one ncclGroup + one unpack kernel per exchange, whole run replayed
+as a CUDA graph) vs the MPI-like host backend over gloo (--with-cpu, small edges only).
 
 For every tile edge E the image is (grid_rows*E) x (grid_cols*E) grey pixels, so every rank owns
 an E x E tile. Reported per backend: device time per iteration (max over ranks), the same tile's
@@ -25,16 +28,19 @@ def main():
     ap.add_argument("--edges", default="256,512,1024,2048,4096,8192,16384")
     ap.add_argument("--loops", type=int, default=40)
     ap.add_argument("--halo-depth", type=int, default=1)
-    ap.add_argument("--backends", default="fused,nccl")
+    ap.add_argument("--backends", default="fused:resident,fused:stream,nccl",
+                    help="comma list of backend[:mode]; cpu = the MPI-like host backend over gloo")
+    ap.add_argument("--with-cpu", action="store_true", help="add the gloo host backend for edges <= 1024")
     ap.add_argument("--channels", type=int, default=1)
     a = ap.parse_args()
+    os.environ.setdefault("PCONV_NCCL_GRAPH", "1")     # the NCCL arm at its best: graph replay
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
     from parallel_convolution_b200 import ConvEngine
     from parallel_convolution_b200.ops import host as H
     gr, gc, _ = H.choose_grid(1 << 20, 1 << 20, world)        # square-image grid for this world size
@@ -42,25 +48,35 @@ def main():
     for E in [int(v) for v in a.edges.split(",")]:
         W, Hh = gc * E, gr * E
         row = {"tile_edge": E, "gpus": world, "grid": f"{gr}x{gc}", "k": a.halo_depth, "loops": a.loops}
-        for be in a.backends.split(","):
-            eng = ConvEngine(width=W, height=Hh, channels=a.channels, filter="gaussian", backend=be,
-                             grid=(gr, gc), halo_depth=a.halo_depth, mode="stream", device=local)
-            best = None
-            for _ in range(3):
-                eng.load_synthetic(1)
-                rep = eng.iterate(a.loops)
-                best = rep.elapsed_ms if best is None else min(best, rep.elapsed_ms)
-            row[be + "_us_per_iter"] = round(best * 1e3 / a.loops, 3)
-            row["halo_bytes_per_exchange"] = eng.grid.halo_bytes_per_iteration(0, a.halo_depth)
-            row.setdefault("waits", {})[be] = round(rep.max_wait_us, 1)
+        arms = a.backends.split(",") + (["cpu"] if a.with_cpu and E <= 1024 else [])
+        done = []
+        for arm in arms:
+            be, _, mode = arm.partition(":")
+            key = arm.replace(":", "_")
+            try:
+                eng = ConvEngine(width=W, height=Hh, channels=a.channels, filter="gaussian", backend=be,
+                                 grid=(gr, gc), halo_depth=a.halo_depth or None, mode=mode or "auto", device=local)
+                best = None
+                for _ in range(3):
+                    eng.load_synthetic(1)
+                    rep = eng.iterate(a.loops)
+                    best = rep.elapsed_ms if best is None else min(best, rep.elapsed_ms)
+            except (ValueError, RuntimeError) as e:      # e.g. resident mode: the tile does not fit on chip
+                row[key + "_skipped"] = str(e)[:80]
+                continue
+            row[key + "_us_per_iter"] = round(best * 1e3 / a.loops, 3)
+            row[key + "_k"] = rep.plan.get("k", a.halo_depth)
+            row["halo_bytes_per_exchange_k1"] = eng.grid.halo_bytes_per_iteration(0, 1)
+            row.setdefault("waits", {})[key] = round(rep.max_wait_us, 1)
             eng.close()
+            done.append(key)
         # the same tile alone on this GPU (no neighbours, no process group): the compute-only floor
         from parallel_convolution_b200.parallel.decomposition import TileGrid
         from parallel_convolution_b200.parallel.fused import VirtualCluster
         from parallel_convolution_b200.models.filters import Filter
         from parallel_convolution_b200.ops import cuda as K
         vc = VirtualCluster(TileGrid.create(E, E, a.channels, 1), Filter.builtin("gaussian"),
-                            halo_depth=a.halo_depth, mode="stream")
+                            halo_depth=a.halo_depth or None, mode="auto")
         vc.synth(1)
         vc.run(a.loops)
         K.device_sync()
@@ -75,10 +91,8 @@ def main():
             solo = ms if solo is None else min(solo, ms)
         vc.close()
         row["solo_us_per_iter"] = round(solo * 1e3 / a.loops, 3)
-        for be in a.backends.split(","):
-            exposed = max(row[be + "_us_per_iter"] - row["solo_us_per_iter"], 1e-3)
-            row[be + "_exposed_halo_us"] = round(exposed, 3)
-            row[be + "_halo_GBps"] = round(row["halo_bytes_per_exchange"] / exposed / 1e3, 2)
+        for key in done:       # what the neighbours cost per iteration, on top of the same tile alone
+            row[key + "_exposed_halo_us_per_iter"] = round(row[key + "_us_per_iter"] - row["solo_us_per_iter"], 3)
         if rank == 0:
             print(json.dumps(row), flush=True)
         if world > 1:

@@ -248,8 +248,14 @@ def _out_of_core(a, channels: int) -> int:
     import time
     from .models.filters import Filter
     from .ops import host as H
-    if a.backend not in ("auto", "cpu", "host") or int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        sys.stderr.write("pconv: --out-of-core runs on the cpu backend in a single process\n")
+    gpu = a.backend in ("fused", "gpu", "cuda")
+    if a.backend == "auto":
+        from .ops import cuda as K
+        gpu = K.available()
+    if gpu:
+        return _out_of_core_gpu(a, channels)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        sys.stderr.write("pconv: --out-of-core on the cpu backend runs in a single process\n")
         return 2
     out_path = a.output
     if out_path is None:
@@ -270,6 +276,43 @@ def _out_of_core(a, channels: int) -> int:
                           "memory_budget_mib": a.out_of_core, "filter": filt.describe(), "output": out_path}))
     else:
         print(f"{dt:f}")
+    return 0
+
+
+def _out_of_core_gpu(a, channels: int) -> int:
+    """``--out-of-core MiB`` on the GPU: strips of the file stream through the device with k-deep halos,
+    file I/O, H2D, iterations and D2H overlapped; with ``-np N`` every rank takes every N-th strip
+    (utils/out_of_core.py)."""
+    from .models.filters import Filter
+    from .utils import out_of_core as ooc
+    dist = _init_dist("fused")
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    out_path = a.output
+    if out_path is None:
+        d, b = os.path.split(a.image)
+        out_path = os.path.join(d, "blur_" + b)
+    try:
+        filt = Filter.parse(a.filter)
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        info = ooc.run_file(a.image, out_path, a.width, a.height, channels, filt, a.loops,
+                            max(1, a.out_of_core) << 20, k=a.halo_depth or None, device=local, rank=rank,
+                            world=world, dist=dist)
+    except (OSError, ValueError, RuntimeError) as e:
+        sys.stderr.write(f"pconv: {e}\n")
+        return 1
+    finally:
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+    if rank == 0:
+        if a.json:
+            info.update({"iterations": a.loops, "backend": "fused (gpu out of core)", "memory_budget_mib": a.out_of_core,
+                         "mpixels_per_s": a.width * a.height * a.loops / max(info["seconds"], 1e-9) / 1e6,
+                         "filter": filt.describe(), "output": out_path})
+            print(json.dumps(info))
+        else:
+            print(f"{info['seconds']:f}")
     return 0
 
 

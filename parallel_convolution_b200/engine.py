@@ -46,6 +46,7 @@ class EngineConfig:
     device: int | None = None        # CUDA device index (default: LOCAL_RANK or 0)
     timeout_ms: float = 10_000.0     # in-kernel watchdog for neighbour flags
     slots: int = 1                   # buffer sets for pipelined streaming steps (H2D || iterate || D2H)
+    standalone: bool = False         # ignore torch.distributed: a private single-process engine inside a rank
 
 
 @dataclass
@@ -84,7 +85,7 @@ class ConvEngine:
         cfg = config or EngineConfig(width=width, height=height, channels=channels, filter=filter, **kw)
         self.cfg = cfg
         self.filter = cfg.filter if isinstance(cfg.filter, Filter) else Filter.parse(str(cfg.filter))
-        self.dist = _dist()
+        self.dist = None if cfg.standalone else _dist()
         self.world = self.dist.get_world_size() if self.dist else 1
         self.rank = self.dist.get_rank() if self.dist else 0
         self.distributed = self.world > 1
@@ -193,12 +194,85 @@ class ConvEngine:
         have = H.file_size(path)
         if have < need:
             raise ValueError(f"{path}: {have} bytes, need {need} for {g.width}x{g.height}x{C}")
+        if self.backend != "cpu" and hasattr(self._impl, "mems"):
+            return self._load_file_pipelined(path)
         tiles = {t.rank: H.read_rect(path, g.row_bytes, t.row0, t.rows, t.col0 * C, t.cols * C)
                  for t in self.local_tiles}
         if self.backend == "cpu":
             self._impl.load(tiles[self._impl.tile.rank])
         else:
             self._impl.upload(tiles)
+
+    # -- overlapped rank-parallel file I/O of the GPU backends ------------------------------------------
+    # The reference's ranks seek/read (write) their own tile rows concurrently (mpi/mpi_conv.c:133-147,
+    # 253-271); here every rank additionally overlaps its pread/pwrite with its PCIe copies: the tile moves
+    # in row chunks through two pinned staging buffers, the disk side of chunk j+1 running while the copy
+    # engine moves chunk j.
+    _IO_CHUNK_BYTES = 8 << 20
+
+    def _io_staging(self, tile_cb: int):
+        import ctypes
+        from .ops import cuda as K
+        rows = max(16, self._IO_CHUNK_BYTES // max(tile_cb, 1))
+        ptrs = [K.host_alloc(rows * tile_cb) for _ in range(2)]
+        bufs = [np.ctypeslib.as_array((ctypes.c_uint8 * (rows * tile_cb)).from_address(p)).reshape(rows, tile_cb)
+                for p in ptrs]
+        return rows, ptrs, bufs
+
+    def _load_file_pipelined(self, path: str) -> None:
+        from .ops import cuda as K
+        g, C, rt = self.grid, self.grid.channels, self._impl
+        if hasattr(rt, "_barrier"):
+            rt._barrier()                 # previous run's readers are done with my buffers
+        for t in self.local_tiles:
+            cb = t.cols * C
+            rows, ptrs, bufs = self._io_staging(cb)
+            ev = [K.Event(), K.Event()]
+            try:
+                for j, r0 in enumerate(range(0, t.rows, rows)):
+                    b, n = j & 1, min(rows, t.rows - r0)
+                    if j >= 2:
+                        ev[b].synchronize()                  # the copy out of this staging buffer is done
+                    H.read_rect(path, g.row_bytes, t.row0 + r0, n, t.col0 * C, cb, out=bufs[b][:n])
+                    K.memcpy2d_async(rt.mems[t.rank].bufs[0] + r0 * rt.pitch, rt.pitch, ptrs[b], cb, cb, n,
+                                     K.H2D, rt.stream)
+                    ev[b].record(rt.stream)
+                K.stream_sync(rt.stream)
+            finally:
+                for p in ptrs:
+                    K.host_free(p)
+        rt.parity = 0
+        if hasattr(rt, "slot"):
+            rt.slot = 0
+
+    def _save_file_pipelined(self, path: str) -> None:
+        from .ops import cuda as K
+        g, C, rt = self.grid, self.grid.channels, self._impl
+        K.stream_sync(rt.stream)
+        slot = getattr(rt, "slot", 0)
+        for t in self.local_tiles:
+            cb = t.cols * C
+            rows, ptrs, bufs = self._io_staging(cb)
+            ev = [K.Event(), K.Event()]
+            src = rt.mems[t.rank].bufs[2 * slot + rt.parity]
+            chunks = [(r0, min(rows, t.rows - r0)) for r0 in range(0, t.rows, rows)]
+            try:
+                for j, (r0, n) in enumerate(chunks):
+                    b = j & 1
+                    K.memcpy2d_async(ptrs[b], cb, src + r0 * rt.pitch, rt.pitch, cb, n, K.D2H, rt.stream)
+                    ev[b].record(rt.stream)
+                    if j >= 1:                               # write chunk j-1 while chunk j comes down
+                        pr0, pn = chunks[j - 1]
+                        ev[1 - b].synchronize()
+                        H.write_rect(path, g.row_bytes, t.row0 + pr0, t.col0 * C, bufs[1 - b][:pn])
+                if chunks:
+                    lr0, ln = chunks[-1]
+                    ev[(len(chunks) - 1) & 1].synchronize()
+                    H.write_rect(path, g.row_bytes, t.row0 + lr0, t.col0 * C, bufs[(len(chunks) - 1) & 1][:ln])
+            finally:
+                K.stream_sync(rt.stream)
+                for p in ptrs:
+                    K.host_free(p)
 
     def load_synthetic(self, seed: int = 1) -> None:
         """Deterministic random image, generated per tile (on the device for GPU backends)."""
@@ -240,7 +314,7 @@ class ConvEngine:
         if not self.distributed:
             return v
         import torch
-        dev = "cpu" if self.dist.get_backend() == "gloo" else f"cuda:{self.device}"
+        dev = "cpu" if (self.backend == "cpu" or self.dist.get_backend() == "gloo") else f"cuda:{self.device}"
         t = torch.tensor([v], dtype=torch.float64, device=dev)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
@@ -280,9 +354,12 @@ class ConvEngine:
             H.create_file(path, g.height * g.row_bytes)
         if self.distributed:
             self.dist.barrier()
-        for r, tile in self.local_results().items():
-            t = g.tile(r)
-            H.write_rect(path, g.row_bytes, t.row0, t.col0 * C, np.ascontiguousarray(tile))
+        if self.backend != "cpu" and hasattr(self._impl, "mems"):
+            self._save_file_pipelined(path)
+        else:
+            for r, tile in self.local_results().items():
+                t = g.tile(r)
+                H.write_rect(path, g.row_bytes, t.row0, t.col0 * C, np.ascontiguousarray(tile))
         if self.distributed:
             self.dist.barrier()
 
@@ -356,6 +433,13 @@ class ConvEngine:
             K.memcpy2d_async(o.ctypes.data, o.shape[1], rt.mems[r].bufs[2 * rt.slot + rt.parity], rt.pitch,
                              o.shape[1], o.shape[0], K.D2H, rt.stream)
         return n + launches
+
+    def slot_sync(self, slot: int) -> None:
+        """Wait for the pipelined step that last used buffer slot ``slot`` (its result is on the host)."""
+        if hasattr(self._impl, "slot_sync"):
+            self._impl.slot_sync(slot)
+        else:
+            self.synchronize()
 
     def synchronize(self) -> None:
         from .ops import cuda as K

@@ -133,6 +133,12 @@ class FusedRuntime:
         my buffers). Call before overwriting a tile buffer in-stream. Returns kernels launched."""
         if not self.multi or self.epoch == 0:
             return 0
+        if getattr(self, "_last_exchanges", 0) >= 1:
+            # The previous run was a persistent launch with at least one in-kernel exchange: a neighbour reads
+            # my input buffer only in its initial region load, BEFORE it pushes its first halo, and my kernel
+            # could not finish without receiving that push — so every neighbour is done with the buffer by
+            # the time this (stream-ordered) point is reached. No flag round trip needed.
+            return 0
         for d in self.drivers.values():
             K.sync_launch(d.sync_params(self.epoch, 0), self.stream)
         return len(self.drivers)
@@ -322,6 +328,7 @@ class FusedRuntime:
         if self.multi:
             self.epoch += 1
         self.cta_epoch += nblocks - 1     # contiguous epochs: the inbox parity keeps alternating
+        self._last_exchanges = nblocks - 1
         self.parity ^= 1                  # reads one buffer of the pair, writes the other
         return plan, len(self.local_ranks)
 
@@ -345,6 +352,7 @@ class FusedRuntime:
         from .fused import BANK1
         ff = [self.mems[r].flags + BANK1 for r in self.local_ranks] if (bank1 and first_wait) else None
         K.stream_run(blocks, n, ks, self.epoch, self.multi, self.stream, first_wait, ff)
+        self._last_exchanges = 0
         self.epoch += len(ks)
         self.parity ^= len(ks) & 1
         return plan, len(ks) * n
@@ -401,6 +409,12 @@ class FusedRuntime:
                              self.pitch, o.shape[1], o.shape[0], K.D2H, s_out)
         P["out_done"][slot].record(s_out)
         return n + launches
+
+    def slot_sync(self, slot: int) -> None:
+        """Block until the pipelined step that last used buffer slot ``slot`` has delivered its result to the
+        host (its D2H copy is complete) — finer than ``pipeline_sync``: later steps keep running."""
+        if self._pipe is not None and self._pipe["used"][slot]:
+            self._pipe["out_done"][slot].synchronize()
 
     def pipeline_sync(self) -> None:
         K.stream_sync(self.stream)
