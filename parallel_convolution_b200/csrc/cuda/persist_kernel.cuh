@@ -393,7 +393,7 @@ persist_kernel(const __grid_constant__ PersistArgs A) {
 #pragma unroll
                     for (int d = 0; d < 9; ++d)
                         if (d != 4 && A.sync.remote_flags[d] != nullptr)
-                            st_release_sys(A.sync.remote_flags[d], A.sync.signal_value);
+                            st_relaxed_sys(A.sync.remote_flags[d], A.sync.signal_value);
                 }
             }
         }

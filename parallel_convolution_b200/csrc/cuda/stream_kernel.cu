@@ -40,7 +40,7 @@ __global__ void sync_kernel(const pconv_sync_t S) {
         __threadfence_system();
 #pragma unroll
         for (int d = 0; d < 9; ++d)
-            if (d != 4 && S.remote_flags[d] != nullptr) st_release_sys(S.remote_flags[d], S.signal_value);
+            if (d != 4 && S.remote_flags[d] != nullptr) st_relaxed_sys(S.remote_flags[d], S.signal_value);
     }
 }
 

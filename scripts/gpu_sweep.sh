@@ -13,7 +13,7 @@ try:
     print({k:d.get(k) for k in ('value','ms_per_step','verified','gpu_launches','n_gpus')}, 'e2e', d['e2e']['ms_per_step'], d['config']['kernel_mode'], d['config']['plan'], d['config']['autotune'], d['config'].get('exchange_probe'))
 except Exception as e: print('bench parse failed', e)
 PY
-TMO=120 PCONV_NCCL_GRAPH=1 run bench.py --gpus $N --steps 20 --warmup 5 --backend nccl > $OUT/bench_nccl.json 2> $OUT/bench_nccl.err; echo "bench nccl(graph) rc=$?"
+TMO=120 run bench.py --gpus $N --steps 20 --warmup 5 --backend nccl > $OUT/bench_nccl.json 2> $OUT/bench_nccl.err; echo "bench nccl(eager) rc=$?"
 python - $OUT/bench_nccl.json <<'PY'
 import json,sys
 try:
