@@ -6,6 +6,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <tuple>
 
 #include "persist_kernel.cuh"
 
@@ -97,12 +98,29 @@ extern "C" int pconv_persist_capacity(const pconv_persist_params_t* p) {
     if (!fn) return pconv_rt::fail("unsupported (filter kind, channels, band height, warps) combination");
     const size_t smem = smem_bytes(p->W, x);
     if ((int)smem > pconv_rt::max_optin_smem()) return pconv_rt::fail("inbox does not fit in shared memory");
-    cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "cudaFuncSetAttribute(persist_kernel)");
+    // per (device, kernel instance, shared-memory size): the attribute and the occupancy query cost tens of
+    // microseconds of host time — too much to repeat on every launch of a 200 us step
+    static std::mutex mu;
+    static std::map<std::tuple<int, const void*, size_t>, int> cache;     // -> resident CTAs
+    static std::map<std::pair<int, const void*>, size_t> limit;           // largest dynamic smem allowed so far
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const auto key = std::make_tuple(dev, (const void*)fn, smem);
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    size_t& lim = limit[std::make_pair(dev, (const void*)fn)];
+    if (smem > lim) {      // only ever RAISE the limit: a cached smaller plan must not lower it under a larger one
+        cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "cudaFuncSetAttribute(persist_kernel)");
+        lim = smem;
+    }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, p->W * 32, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, p->W * 32, smem);
     if (e != cudaSuccess) return pconv_rt::fail_cuda(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
-    return per_sm * pconv_rt::sm_count();
+    const int cap = per_sm * pconv_rt::sm_count();
+    cache[key] = cap;
+    return cap;
 }
 
 extern "C" int pconv_persist_launch(const pconv_persist_params_t* p, void* stream) {

@@ -309,10 +309,21 @@ class FusedRuntime:
         first_wait, self._first_wait = getattr(self, "_first_wait", 0), 0
         signal = self.epoch + 1 if self.multi else 0
         bank1, self._first_bank1 = getattr(self, "_first_bank1", False), False
-        params = {r: self.drivers[r].persist_params(plan, loops, self.parity, first_wait if self.multi else 0,
-                                                    signal, self.cta_epoch, slot=self.slot,
-                                                    wait_bank1=bank1, peer_scope=self.world > 1)
-                  for r in self.local_ranks}
+        # the launch structs are cached per (plan, loops, buffers, flag bank): only the epochs change per run
+        ckey = (plan, loops, self.parity, self.slot, bank1)
+        cache = self.__dict__.setdefault("_pparams", {})
+        if ckey not in cache:
+            if len(cache) > 64:
+                cache.clear()
+            cache[ckey] = {r: self.drivers[r].persist_params(plan, loops, self.parity, 0, 0, 0, slot=self.slot,
+                                                             wait_bank1=bank1, peer_scope=self.world > 1)
+                           for r in self.local_ranks}
+        params = cache[ckey]
+        for r, p in params.items():
+            p.sync.inject_drop_signal = 1 if self.drivers[r].inject_drop_signal else 0
+            p.sync.wait_value = first_wait if self.multi else 0
+            p.sync.signal_value = signal
+            p.epoch_base = self.cta_epoch & 0xFFFFFFFF
         if self._rank_streams:
             fork = K.Event().record(self.stream)
             joins = []

@@ -22,7 +22,11 @@ KERNELS = {
     "stream_sep121_grey_R14": ("stream_kind_sep.cu.o", "_ZN5pconv13stream_kernelILi2ELi1ELi14EEEvNS_10StreamArgsE"),
     "stream_int_rgb_R10": ("stream_kind_int.cu.o", "_ZN5pconv13stream_kernelILi1ELi3ELi10EEEvNS_10StreamArgsE"),
     "stream_f32_grey_R8": ("stream_kind_f32.cu.o", "_ZN5pconv13stream_kernelILi0ELi1ELi8EEEvNS_10StreamArgsE"),
-    "resident_sep121_rgb_R14": ("resident_kind_sep.cu.o", "_ZN5pconv15resident_kernelILi2ELi3ELi14EEEvNS_12ResidentArgsE"),
+    "persist_sep121_rgb_R14_W16": ("persist_sep_w16.cu.o", "_ZN5pconv14persist_kernelILi2ELi3ELi14ELi16EEEvNS_11PersistArgsE"),
+    "persist_sep121_rgb_R7_W8": ("persist_sep_w8.cu.o", "_ZN5pconv14persist_kernelILi2ELi3ELi7ELi8EEEvNS_11PersistArgsE"),
+    "persist_sep121_grey_R14_W16": ("persist_sep_w16.cu.o", "_ZN5pconv14persist_kernelILi2ELi1ELi14ELi16EEEvNS_11PersistArgsE"),
+    "persist_int_rgb_R10_W16": ("persist_int_w16.cu.o", "_ZN5pconv14persist_kernelILi1ELi3ELi10ELi16EEEvNS_11PersistArgsE"),
+    "persist_f32_grey_R8_W16": ("persist_f32_w16.cu.o", "_ZN5pconv14persist_kernelILi0ELi1ELi8ELi16EEEvNS_11PersistArgsE"),
 }
 
 
@@ -36,6 +40,45 @@ def opcode(line):
     body = re.sub(r"/\*[0-9a-f]+\*/", "", line).strip()
     body = re.sub(r"^@!?U?P[0-9T]+\s+", "", body)
     return body.split()[0].rstrip(";") if body else ""
+
+
+def segment_report(rep_path, out_path):
+    """Warp-stall samples of a persistent-kernel capture, aggregated between its synchronisation points
+    (barriers, fences, bulk copy, mbarrier): where the time of an exchange goes, from the ncu source page."""
+    src = subprocess.run(["ncu", "-i", rep_path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(src.splitlines()))
+    if len(rows) < 4:
+        return
+    hdr, data = rows[1], rows[2:]
+    ci = {n: i for i, n in enumerate(hdr)}
+    if "# Samples" not in ci:
+        return
+    S, SRC, IE = ci["# Samples"], ci["Source"], ci["Instructions Executed"]
+    stalls = [c for c in hdr if c.startswith("stall_") and "Not Issued" not in c]
+    tot = sum(int(r[S]) for r in data) or 1
+    segs, acc, start = [], 0, 0
+    for i, r in enumerate(data):
+        acc += int(r[S])
+        if any(m in r[SRC] for m in ("BAR.SYNC", "UBLKCP", "SYNCS.ARRIVE", "MEMBAR.ALL.GPU", "MEMBAR.ALL.SYS", "NANOSLEEP")):
+            segs.append((start, i + 1, acc, r[SRC].strip()[:44]))
+            acc, start = 0, i + 1
+    segs.append((start, len(data), acc, "end"))
+    with open(out_path, "w") as f:
+        f.write(f"# {rows[0][1] if len(rows[0]) > 1 else ''}\n# {os.path.basename(rep_path)}: {tot} warp-stall samples over {len(data)} SASS instructions\n")
+        f.write("# segment = instructions up to and including the named synchronisation instruction\n")
+        for a, b, n, label in segs:
+            if n < tot * 0.003:
+                continue
+            st = {c: sum(int(data[j][ci[c]]) for j in range(a, b)) for c in stalls}
+            top = sorted(st.items(), key=lambda kv: -kv[1])[:3]
+            ie = sum(int(data[j][IE]) for j in range(a, b))
+            f.write(f"instr[{a:5d},{b:5d})  samples {n:6d} ({100 * n / tot:5.1f} %)  warp-instructions {ie:10d}  ends at {label:44s} "
+                    f"top stalls: {', '.join(k.replace('stall_', '') + '=' + str(v) for k, v in top)}\n")
+        worst = sorted(range(len(data)), key=lambda j: -int(data[j][S]))[:12]
+        f.write("# hottest instructions\n")
+        for j in sorted(worst):
+            f.write(f"  [{j:5d}] {int(data[j][S]):6d}  {data[j][SRC].strip()[:90]}\n")
+    print("wrote", out_path)
 
 
 def main():
@@ -59,9 +102,10 @@ def main():
         with open(os.path.join(OUT, f"sass_{name}.txt"), "w") as f:
             f.write(f"# {fn}\n# cuobjdump -sass of parallel_convolution_b200/_lib/{obj} (sm_100a), {len(L)} instructions\n")
             f.write("# whole-kernel opcode histogram: " + ", ".join(f"{k}:{v}" for k, v in sorted(hist.items(), key=lambda kv: -kv[1])[:14]) + "\n")
-            proto = [l for l in L if re.search(r"STRONG\.SYS|\.SYS|MEMBAR|ATOM|CCTL|NANOSLEEP|GLOBALTIMER|ERRBAR|FENCE", l)]
-            f.write("#\n# --- halo protocol instructions (system-scope flags, fences, peer-visible loads/stores) ---\n")
-            f.write("\n".join(proto[:60]) + "\n")
+            proto = [l for l in L if re.search(r"STRONG\.SYS|\.SYS|MEMBAR|ATOM|CCTL|NANOSLEEP|GLOBALTIMER|ERRBAR|FENCE|UBLKCP|SYNCS|UTMA", l)]
+            f.write("#\n# --- halo protocol instructions: system/gpu-scope flags and fences, bulk async copy (UBLKCP = "
+                    "cp.async.bulk), mbarrier (SYNCS.*) ---\n")
+            f.write("\n".join(proto[:80]) + "\n")
             ldst = [l for l in L if re.search(r"LDG\.E\.128|STG\.E\.128", l)]
             f.write(f"#\n# --- 128-bit global accesses (tile / peer-tile rows straight to/from registers): {len(ldst)} sites ---\n")
             f.write("\n".join(ldst[:12]) + "\n")
@@ -112,11 +156,12 @@ def main():
             "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
             "smsp__average_warps_issue_stalled", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput", "lts__throughput"]
-    gdir = os.path.join(ROOT, "gpurun_out")
+    gdir = os.path.join(ROOT, "gpurun_out", sys.argv[1] if len(sys.argv) > 1 else "final_r2")
     for rep in sorted(os.listdir(gdir)) if os.path.isdir(gdir) else []:
         if not rep.endswith(".ncu-rep"):
             continue
         raw = subprocess.run(["ncu", "-i", os.path.join(gdir, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        segment_report(os.path.join(gdir, rep), os.path.join(OUT, f"ncu_{rep[:-8]}_segments.txt"))
         rows = list(csv.reader(raw.splitlines()))
         if len(rows) < 3:
             continue

@@ -87,6 +87,19 @@ def test_decomposition_invariance(rng, workers, grid, c):
         assert np.array_equal(out, ref), (workers, grid, c, name)
 
 
+@pytest.mark.parametrize("h,w,c,grid,k", [(40, 64, 1, (4, 1), 4), (48, 2048, 3, (8, 1), 4), (64, 300, 1, (1, 4), 3),
+                                          (36, 96, 3, (3, 3), 2)])
+def test_small_tiles_in_deep_grids(rng, h, w, c, grid, k):
+    """Tiles much smaller than a CTA region in grids three or more tiles deep: the region overhangs the
+    ADJACENT tile, and what lies beyond it belongs to a tile two steps away — it must be treated as zero,
+    never read (it would fall outside that neighbour's buffer). Run under compute-sanitizer memcheck by
+    scripts/sanitize.sh."""
+    img = random_image(rng, h, w, c)
+    f = Filter.builtin("gaussian")
+    out = _run(img, f, 2 * k + 1, workers=grid[0] * grid[1], grid=grid, halo_depth=k)
+    assert np.array_equal(out, host.cpu_run_image(img, f.spec, 2 * k + 1))
+
+
 def test_remainder_tiles(rng):
     img = random_image(rng, 101, 203, 3)   # not divisible by anything useful
     f = Filter.builtin("gaussian")
