@@ -1,9 +1,12 @@
 """Roofline terms for a run: which bound is the relevant one and how far the run is from it.
 
-Denominators are MEASURED (``MEASURED_PEAKS.json`` when present: HBM copy bandwidth; the profiling
-recipe's 770 GB/s NVLink peer-copy figure) except the integer-issue bound of the SWAR kernels,
-which is a model: ops per output byte of each arithmetic path over the two integer-capable issue
-pipes of an SM (profiles/README.md). Every fraction is labelled accordingly.
+Denominators are MEASURED: ``MEASURED_PEAKS.json`` when present (HBM copy bandwidth), the profiling
+recipe's 770 GB/s NVLink peer-copy figure, and — for the Gaussian SWAR path, the headline — the issue
+peak of the kernel's own instruction mix (``scripts/microbench/issue_peak.cu``: the same ``band_sep121``
+code iterated on registers only, 16 warps per SM; 28.8 B/clk/SM for RGB, 29.8 for grey on B200,
+``profiles/microbench.txt``), at the SM clock sampled during the run. The integer-IMAD and exact-fp32
+paths still use a modelled bound (ops per output byte over the two integer-capable issue pipes).
+Every term is labelled accordingly.
 """
 from __future__ import annotations
 
@@ -12,8 +15,10 @@ import os
 
 NVLINK_GBS = 770.0            # measured peer copy, per direction per GPU (B200_PROFILING.md)
 HBM_GBS_FALLBACK = 6650.0     # the recipe's fallback when MEASURED_PEAKS.json is absent
-# modelled region bytes per clock per SM at perfect dual-pipe issue (15 / ~32 / ~88 lane-ops per 4 B)
-ALU_BYTES_PER_CLK = {"sep121-swar": 34.0, "int-swar": 16.0, "f32-exact": 6.0}
+# region bytes per clock per SM: measured issue peak (sep121) / modelled dual-pipe bound (~32 / ~88 lane-ops per 4 B)
+ALU_BYTES_PER_CLK = {"sep121-swar": 28.8, "int-swar": 16.0, "f32-exact": 6.0}
+ALU_PEAK_SOURCE = {"sep121-swar": "measured: scripts/microbench/issue_peak.cu (profiles/microbench.txt)",
+                   "int-swar": "modelled bound, not a measured peak", "f32-exact": "modelled bound, not a measured peak"}
 SM_CLOCK_HZ = 1.9e9
 
 
@@ -39,7 +44,7 @@ def terms(width: int, height: int, channels: int, loops: int, gpus: int, k: int,
         "hbm_peak": f"{hbm:.0f} GB/s ({src})",
         "nvlink_halo_s": halo_bytes_per_exchange * (loops / k) / (NVLINK_GBS * 1e9),
         "int_issue_s": img * loops / gpus / (ALU_BYTES_PER_CLK[path] * sms * clock),
-        "int_issue_note": "modelled bound, not a measured peak",
+        "int_issue_note": ALU_PEAK_SOURCE[path],
     }
 
 

@@ -24,9 +24,7 @@ KERNELS = {
     "stream_f32_grey_R8": ("stream_kind_f32.cu.o", "_ZN5pconv13stream_kernelILi0ELi1ELi8EEEvNS_10StreamArgsE"),
     "persist_sep121_rgb_R14_W16": ("persist_sep_w16.cu.o", "_ZN5pconv14persist_kernelILi2ELi3ELi14ELi16EEEvNS_11PersistArgsE"),
     "persist_sep121_rgb_R7_W8": ("persist_sep_w8.cu.o", "_ZN5pconv14persist_kernelILi2ELi3ELi7ELi8EEEvNS_11PersistArgsE"),
-    "persist_sep121_grey_R14_W16": ("persist_sep_w16.cu.o", "_ZN5pconv14persist_kernelILi2ELi1ELi14ELi16EEEvNS_11PersistArgsE"),
     "persist_int_rgb_R10_W16": ("persist_int_w16.cu.o", "_ZN5pconv14persist_kernelILi1ELi3ELi10ELi16EEEvNS_11PersistArgsE"),
-    "persist_f32_grey_R8_W16": ("persist_f32_w16.cu.o", "_ZN5pconv14persist_kernelILi0ELi1ELi8ELi16EEEvNS_11PersistArgsE"),
 }
 
 
