@@ -50,6 +50,30 @@ NVCCFLAGS = ["-ccbin", CXX, "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=
              "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--fmad=false"]
 
 
+class _BuildLock:
+    """Exclusive lock around every build: N torchrun ranks importing the package with a stale content hash
+    must not compile into the same _lib/ paths at once (a rank could dlopen a half-written library)."""
+
+    def __enter__(self):
+        import fcntl
+        LIB.mkdir(exist_ok=True)
+        self.f = open(LIB / ".build.lock", "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
+
+
+def _link(cmd_prefix: list[str], target: Path, inputs: list[str], libs: list[str]) -> None:
+    """Link to a temporary name and rename: readers never see a partially written artefact."""
+    tmp = target.with_name(target.name + f".tmp{os.getpid()}")
+    _run([*cmd_prefix, "-o", str(tmp), *inputs, *libs])
+    os.replace(tmp, target)
+
+
 def _run(cmd: list[str], log: Path | None = None) -> None:
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if log is not None:
@@ -91,6 +115,13 @@ def build_host(force: bool = False) -> Path:
     srcs = [CSRC / s for s in HOST_SOURCES] + [CSRC / HOST_ORACLE]
     if not force and not _stale(HOST_LIB, srcs + _all_headers(), CXXFLAGS):
         return HOST_LIB
+    with _BuildLock():
+        if not force and not _stale(HOST_LIB, srcs + _all_headers(), CXXFLAGS):
+            return HOST_LIB      # another rank built it while we waited for the lock
+        return _build_host_locked(srcs)
+
+
+def _build_host_locked(srcs: list[Path]) -> Path:
     objs = []
     for s in HOST_SOURCES:
         o = LIB / (Path(s).stem + ".o")
@@ -100,7 +131,7 @@ def build_host(force: bool = False) -> Path:
     _run([CXX, "-std=c++17", "-fPIC", "-O1", "-ffp-contract=off", "-fno-tree-vectorize",
           "-c", str(CSRC / HOST_ORACLE), "-o", str(o)])
     objs.append(str(o))
-    _run([CXX, "-shared", "-fopenmp", "-o", str(HOST_LIB), *objs])
+    _link([CXX, "-shared", "-fopenmp"], HOST_LIB, objs, [])
     _stamp(HOST_LIB, srcs + _all_headers(), CXXFLAGS)
     return HOST_LIB
 
@@ -121,6 +152,13 @@ def build_cuda(force: bool = False) -> Path:
     srcs = [CSRC / s for s in CUDA_SOURCES if (CSRC / s).exists()]
     if not force and not _stale(CUDA_LIB, srcs + _all_headers(), NVCCFLAGS):
         return CUDA_LIB
+    with _BuildLock():
+        if not force and not _stale(CUDA_LIB, srcs + _all_headers(), NVCCFLAGS):
+            return CUDA_LIB
+        return _build_cuda_locked(srcs, force)
+
+
+def _build_cuda_locked(srcs: list[Path], force: bool) -> Path:
     if not Path(NVCC).exists():
         raise RuntimeError(f"nvcc not found at {NVCC}; the CUDA library cannot be built")
     from concurrent.futures import ThreadPoolExecutor
@@ -135,8 +173,8 @@ def build_cuda(force: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, len(srcs))) as ex:   # the kernel TUs take minutes
         objs = list(ex.map(compile_one, srcs))
-    _run([NVCC, "-ccbin", CXX, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(CUDA_LIB),
-          *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"])
+    _link([NVCC, "-ccbin", CXX, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"], CUDA_LIB, objs,
+          ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
     _stamp(CUDA_LIB, srcs + _all_headers(), NVCCFLAGS)
     return CUDA_LIB
 
