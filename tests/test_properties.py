@@ -116,3 +116,29 @@ def test_emulated_exchange_random_geometry(h, wpx, c, k, R, warps, loops, seed):
         assert got in (-2,)
         return
     assert np.array_equal(got, host.oracle(img, f.spec, loops))
+
+
+@settings(max_examples=60, deadline=None)
+@given(k=st.integers(1, 20), TH=st.integers(1, 220), nh=st.integers(1, 4), nty=st.integers(1, 30), ntx=st.integers(1, 30))
+def test_arena_size_formula_matches_the_native_layout(k, TH, nh, nty, ntx):
+    """parallel/fused.py:persist_arena_bytes mirrors csrc/common/xplan.h (xp_finish + xp_arena_bytes), which
+    the native launcher evaluates for the same plan: flags area + two parities of one slot per CTA."""
+    from parallel_convolution_b200.parallel.fused import persist_arena_bytes
+    from parallel_convolution_b200.parallel.plan import StreamPlan
+    HB = 16 * nh
+    p = StreamPlan(k, 4, TH, 512 - 2 * HB, HB, ntx, nty, 1, 0.0, 8)
+    nc = (512 - 2 * HB) // 16
+    chunks = (2 * k * nc + 2 * TH * nh + 4 * k * nh + 7) // 8 * 8
+    assert persist_arena_bytes(p) == 1024 * 16 * 4 + 2 * nty * ntx * chunks * 16
+
+
+@settings(max_examples=80, deadline=None)
+@given(height=st.integers(1, 100000), rb=st.integers(1, 200000), loops=st.integers(1, 500),
+       mem=st.integers(1 << 16, 1 << 34), k=st.one_of(st.none(), st.integers(1, 64)))
+def test_out_of_core_strip_plan(height, rb, loops, mem, k):
+    """GPU out-of-core: strips cover the image, carry a halo no deeper than themselves, k never exceeds loops."""
+    from parallel_convolution_b200.utils.out_of_core import plan_strips
+    S, kp = plan_strips(height, rb, loops, mem, k)
+    assert 1 <= kp <= loops and (k is None or kp <= k)
+    assert 1 <= S <= height
+    assert S >= min(height, 2 * kp)          # a strip is at least as deep as its two halos together
