@@ -100,8 +100,25 @@ struct Sep121Path {
     }
     // push row r+1 when output row r lies outside the image (it stays zero): state update only
     __device__ __forceinline__ void skip(const uint4& w) { prime1(w); }
+    // Result pack: sum << 4 puts the result byte into the high half of each 16-bit lane, one PRMT packs four.
+    // LANES (kMaskLanes): the shift is a multiply by a per-lane factor, 16 in lanes whose chunk lies inside
+    // the image and 0 in lanes outside — dead lanes then produce zero rows, at exactly the instruction count
+    // of the unmasked code (IMAD with a register factor instead of IMAD.SHL).
     // push row r+1, return output row r
     __device__ __forceinline__ uint4 push(const uint4& w) {
+        uint4 o;
+        push_impl<false>(w, o, 16u);
+        return o;
+    }
+    // push row r+1, output row r with the per-lane factor m16 (16: alive, 0: the lane is outside the image)
+    __device__ __forceinline__ uint4 push_lanes(const uint4& w, uint32_t m16) {
+        uint4 o;
+        push_impl<true>(w, o, m16);
+        return o;
+    }
+
+    template <bool LANES>
+    __device__ __forceinline__ void push_impl(const uint4& w, uint4& dst, uint32_t m16) {
         const uint32_t x[4] = {w.x, w.y, w.z, w.w};
         uint32_t vE[4], vO[4];
 #pragma unroll
@@ -127,7 +144,7 @@ struct Sep121Path {
                 const uint32_t oPrev = j ? vO[j - 1] : oL, eNext = j < 3 ? vE[j + 1] : eR;
                 const uint32_t oE = 2u * vE[j] + lanes_shift(oPrev, vO[j]) + vO[j];
                 const uint32_t oO = 2u * vO[j] + vE[j] + lanes_shift(vE[j], eNext);
-                o[j] = prmt(oE << 4, oO << 4, 0x7351u);
+                o[j] = LANES ? prmt(oE * m16, oO * m16, 0x7351u) : prmt(oE << 4, oO << 4, 0x7351u);
             }
         } else if (C == 4) {
             // RGBA: x +- 4 is the same lane of the adjacent word — no lane shifts at all
@@ -137,7 +154,7 @@ struct Sep121Path {
             for (int j = 0; j < 4; ++j) {
                 const uint32_t oE = 2u * vE[j] + (j ? vE[j - 1] : eL) + (j < 3 ? vE[j + 1] : eR);
                 const uint32_t oO = 2u * vO[j] + (j ? vO[j - 1] : oL) + (j < 3 ? vO[j + 1] : oR);
-                o[j] = prmt(oE << 4, oO << 4, 0x7351u);
+                o[j] = LANES ? prmt(oE * m16, oO * m16, 0x7351u) : prmt(oE << 4, oO << 4, 0x7351u);
             }
         } else {
             const uint32_t eL = __shfl_up_sync(kFull, vE[3], 1), oL = __shfl_up_sync(kFull, vO[3], 1);
@@ -150,10 +167,10 @@ struct Sep121Path {
                 const uint32_t oE = 2u * vE[j] + oPrev + lanes_shift(vO[j], oNext);
                 // odd x = 4j+1, 4j+3: x-3 -> (4j-2, 4j); x+3 -> (4j+4, 4j+6) = E lanes of word j+1
                 const uint32_t oO = 2u * vO[j] + lanes_shift(ePrev, vE[j]) + eNext;
-                o[j] = prmt(oE << 4, oO << 4, 0x7351u);
+                o[j] = LANES ? prmt(oE * m16, oO * m16, 0x7351u) : prmt(oE << 4, oO << 4, 0x7351u);
             }
         }
-        return make_uint4(o[0], o[1], o[2], o[3]);
+        dst = make_uint4(o[0], o[1], o[2], o[3]);
     }
 };
 
@@ -384,13 +401,18 @@ struct F32Path {
 // Zero padding must stay zero, so rows / bytes outside the image are forced back to zero after every
 // iteration — but only where that can happen. MODE is chosen PER WARP (warp-uniform):
 //   0  every row and byte of the band lies inside the image: no masking at all (the common case)
-//   1  rows all inside, some columns of the CTA outside (left / right image edge): column mask only
+//   1  rows all inside, some columns of the CTA outside (left / right image edge) and the edge cuts through
+//      a 16-byte chunk: byte-wise column mask (four LOP3 per row)
 //   2  some band rows outside the image (first / last warp of a CTA at the top / bottom image edge):
 //      those rows are not computed at all (so that warp has LESS work), plus the column mask if needed
+//   3  rows all inside, the image edge is chunk-aligned: every lane's chunk is either entirely inside or
+//      entirely outside the image. The Gaussian path multiplies its sums by a per-lane factor (16 inside,
+//      0 outside) where the unmasked code shifts by 4, so out-of-image lanes produce zero rows at no extra
+//      instruction; the other paths keep their out-of-image lanes with one select per word.
 // A CTA on the image border used to run the fully masked code in all of its warps and was 15-25 %
 // slower than an interior CTA — and in a persistent grid everybody waits for the slowest CTA.
 // ---------------------------------------------------------------------------------------------
-constexpr int kMaskNone = 0, kMaskCols = 1, kMaskRows = 2;
+constexpr int kMaskNone = 0, kMaskCols = 1, kMaskRows = 2, kMaskLanes = 3;
 
 template <int MODE>
 __device__ __forceinline__ uint4 apply_mask(uint4 o, const uint4& cmask, uint32_t rowmask, int i) {
@@ -411,10 +433,13 @@ __device__ __forceinline__ void band_sep121(uint4 (&rows)[R], const uint4& top, 
     Sep121Path<C> p(f);
     p.prime0(top);
     p.prime1(rows[0]);
+    const uint32_t m16 = cmask.x & 16u;    // kMaskLanes: a lane's mask is all ones (factor 16) or all zeros (0)
 #pragma unroll
     for (int i = 0; i < R; ++i) {
         const uint4& nxt = i + 1 < R ? rows[i + 1] : bottom;
-        if (MODE != kMaskRows || ((rowmask >> i) & 1u)) {
+        if (MODE == kMaskLanes) {
+            rows[i] = p.push_lanes(nxt, m16);
+        } else if (MODE != kMaskRows || ((rowmask >> i) & 1u)) {
             uint4 o = p.push(nxt);
             if (MODE == kMaskCols || (MODE == kMaskRows && need_cols)) {
                 o.x &= cmask.x; o.y &= cmask.y; o.z &= cmask.z; o.w &= cmask.w;
@@ -434,7 +459,8 @@ struct PhasedSteps {
         if constexpr (I < R) {
             const uint4 nxt = (I + 1 < R) ? rows[(I + 1 < R) ? I + 1 : 0] : bottom;
             const uint4 o = p.template push<I % 3>(nxt);
-            rows[I] = apply_mask<MODE>(o, cmask, rowmask, I);
+            if constexpr (MODE == kMaskLanes) { if (cmask.x != 0u) rows[I] = o; }
+            else rows[I] = apply_mask<MODE>(o, cmask, rowmask, I);
             PhasedSteps<Path, C, R, MODE, I + 1>::run(p, rows, bottom, cmask, rowmask);
         }
     }
@@ -477,7 +503,14 @@ __device__ __forceinline__ void region_iterate(uint4 (&rows)[R], EdgeBuffersT<W>
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     constexpr uint32_t kAll = (R >= 32) ? 0xffffffffu : ((1u << R) - 1u);
-    const int mode = (rowmask & kAll) != kAll ? kMaskRows : (need_cols ? kMaskCols : kMaskNone);   // warp-uniform
+    // Does the image edge cut through some lane's chunk (CTA-uniform)? Only CTAs at a left / right image edge ask.
+    bool partial = false;
+    if (need_cols) {
+        const uint32_t all = cmask.x & cmask.y & cmask.z & cmask.w, any = cmask.x | cmask.y | cmask.z | cmask.w;
+        partial = __syncthreads_or(all != 0xffffffffu && any != 0u) != 0;
+    }
+    const int mode = (rowmask & kAll) != kAll ? kMaskRows
+                     : (need_cols ? (partial ? kMaskCols : kMaskLanes) : kMaskNone);   // warp-uniform
     for (int it = 0; it < k; ++it) {
         const int par = it & 1;
         eb.row[par][warp][0][lane] = rows[0];
@@ -486,6 +519,7 @@ __device__ __forceinline__ void region_iterate(uint4 (&rows)[R], EdgeBuffersT<W>
         const uint4 top = warp > 0 ? eb.row[par][warp - 1][1][lane] : zero;
         const uint4 bottom = warp < W - 1 ? eb.row[par][warp + 1][0][lane] : zero;
         if (mode == kMaskNone) band_iterate<KIND, C, R, kMaskNone>(rows, top, bottom, cmask, rowmask, need_cols, f);
+        else if (mode == kMaskLanes) band_iterate<KIND, C, R, kMaskLanes>(rows, top, bottom, cmask, rowmask, need_cols, f);
         else if (mode == kMaskCols) band_iterate<KIND, C, R, kMaskCols>(rows, top, bottom, cmask, rowmask, need_cols, f);
         else band_iterate<KIND, C, R, kMaskRows>(rows, top, bottom, cmask, rowmask, need_cols, f);
     }
