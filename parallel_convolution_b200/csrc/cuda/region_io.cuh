@@ -54,6 +54,26 @@ static __device__ __noinline__ uint4 load_chunk_bytes(const pconv_geometry_t& g,
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// A 16-byte chunk that lies inside ONE owner's buffer but not on a 16-byte boundary there (tiles whose width
+// is not a whole number of chunks shift everything the neighbour sees): two aligned 128-bit loads and a
+// 128-bit funnel shift instead of sixteen single-byte loads. The extra bytes read belong to the same
+// allocation (every tile buffer ends with >= 64 bytes of slack) and are discarded.
+static __device__ __noinline__ uint4 load_chunk_unaligned(const uint8_t* a) {
+    const uintptr_t u = reinterpret_cast<uintptr_t>(a);
+    const uint4* q = reinterpret_cast<const uint4*>(u & ~(uintptr_t)15);
+    const uint4 lo = __ldcg(q), hi = __ldcg(q + 1);
+    const uint32_t bs = (uint32_t)(u & 3u) * 8u;
+    uint32_t w0, w1, w2, w3, w4;
+    switch ((u >> 2) & 3u) {       // word shift: uniform over the warp (pitches and chunk steps are multiples of 16)
+        case 0: w0 = lo.x; w1 = lo.y; w2 = lo.z; w3 = lo.w; w4 = hi.x; break;
+        case 1: w0 = lo.y; w1 = lo.z; w2 = lo.w; w3 = hi.x; w4 = hi.y; break;
+        case 2: w0 = lo.z; w1 = lo.w; w2 = hi.x; w3 = hi.y; w4 = hi.z; break;
+        default: w0 = lo.w; w1 = hi.x; w2 = hi.y; w3 = hi.z; w4 = hi.w; break;
+    }
+    return make_uint4(__funnelshift_r(w0, w1, bs), __funnelshift_r(w1, w2, bs), __funnelshift_r(w2, w3, bs),
+                      __funnelshift_r(w3, w4, bs));
+}
+
 // One 16-byte chunk of the image starting at global byte column gb of global row gr: a single
 // 128-bit load through the owning tile's (possibly peer-mapped) pointer — L2-coherent, L1 bypass,
 // because the data was written by other CTAs / other GPUs. Zero outside the image.
@@ -149,7 +169,11 @@ __device__ __forceinline__ void load_band(uint4 (&rows)[R], const pconv_geometry
             if (!((slow >> i) & 1u)) continue;
             const int64_t gr = gr0 + i;
             const int o = owner_of(gr, g.row_lo);
-            rows[i] = load_chunk_bytes(g, s, o, gr - g.row_lo[o], gb);
+            const uint8_t* base = s.p[3 * o + oc];
+            if (one_owner && base != nullptr)      // whole chunk in one buffer, only misaligned there
+                rows[i] = load_chunk_unaligned(base + cofs + (gr - g.row_lo[o]) * s.pitch[3 * o + oc]);
+            else
+                rows[i] = load_chunk_bytes(g, s, o, gr - g.row_lo[o], gb);
         }
     }
 }
