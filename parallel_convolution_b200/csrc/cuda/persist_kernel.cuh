@@ -8,12 +8,15 @@
 // the overlap engine.
 //
 // Exchange b (every k iterations), see common/xplan.h for the geometry:
-//   1. PUSH   every thread stores the chunks of its band that lie in the k-deep border of the CTA's
-//             interior straight from registers into the inbox slot (parity b&1) of each neighbouring CTA
-//             that needs them — plain 128-bit stores; the slot lives on the CONSUMER's GPU, so across
-//             GPUs these are fire-and-forget NVLink writes through the peer-mapped arena.
+//   1. PUSH   the chunks of the k-deep border of the CTA's interior go into the inbox slot (parity b&1) of
+//             each neighbouring CTA that needs them — plain 128-bit stores; the slot lives on the CONSUMER's
+//             GPU, so across GPUs these are fire-and-forget NVLink writes through the peer-mapped arena.
+//             Side borders leave straight from registers (west and east lanes in the same instructions);
+//             the k top / bottom rows are dumped into a shared-memory outbox by the warps that hold them and
+//             pushed by ALL warps, so that no single warp's epilogue paces the CTA.
 //   2. SIGNAL __syncthreads; lanes 0..8 of warp 0 release-store the epoch into "their" neighbour's flag
-//             word (st.release.gpu, or .sys when the neighbour is another GPU).
+//             word (st.release.gpu); neighbours on other GPUs are signalled by warp 1 (st.release.sys waits
+//             for the NVLink writes to be acknowledged and must not delay the local signalling).
 //   3. FETCH  lane 0 arms the CTA's mbarrier with the expected byte count; lanes 0..8 each poll ONE
 //             local flag word (the one their source neighbour writes) and, as soon as it shows the epoch,
 //             issue ONE bulk async copy (cp.async.bulk global -> shared, complete_tx on the mbarrier)

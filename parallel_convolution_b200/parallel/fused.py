@@ -181,8 +181,15 @@ class TileDriver:
         return p
 
     def sync_params(self, wait: int, signal: int, bank: int = 0) -> K.Sync:
-        """Parameters of a stand-alone protocol step on flag bank 0 (launch epochs) or 1 (inputs)."""
-        s = K.Sync()
+        """Parameters of a stand-alone protocol step on flag bank 0 (launch epochs) or 1 (inputs). The struct
+        is cached per bank (this runs once or twice per step of a ~200 us step): only the epochs change."""
+        cache = self.__dict__.setdefault("_sync_cache", {})
+        s = cache.get(bank)
+        if s is not None:
+            s.wait_value, s.signal_value = wait, signal
+            s.inject_drop_signal = 1 if self.inject_drop_signal else 0
+            return s
+        s = cache[bank] = K.Sync()
         off = BANK1 if bank else 0
         s.local_flags = self.mem.flags + off
         for d in range(9):
