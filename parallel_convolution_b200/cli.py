@@ -149,6 +149,9 @@ def main(argv: list[str] | None = None) -> int:
     rank = dist.get_rank() if dist else 0
 
     from .engine import ConvEngine
+    import time as _time
+    t_job = _time.perf_counter()
+    t_load = t_store = 0.0
     out_path = a.output
     if out_path is None:
         d, b = os.path.split(a.image)
@@ -178,6 +181,7 @@ def main(argv: list[str] | None = None) -> int:
             with nvtx_range("pconv:autotune"):
                 eng.autotune(min(a.loops, a.checkpoint_every) if a.checkpoint_every > 0 else a.loops)
         with nvtx_range("pconv:load"):
+            t0_load = _time.perf_counter()
             state = ckpt.load_state(out_path) if a.resume else None
             if state is not None:
                 ckpt.check_compatible(state, a.width, a.height, channels, eng.filter, a.loops)
@@ -187,6 +191,7 @@ def main(argv: list[str] | None = None) -> int:
                 eng.load_synthetic(a.synthetic)
             else:
                 eng.load_file(a.image)
+            t_load = _time.perf_counter() - t0_load
         elapsed_ms, launches, rep = 0.0, 0, None
         with nvtx_range("pconv:iterate"):
             while done < a.loops or rep is None:
@@ -203,7 +208,9 @@ def main(argv: list[str] | None = None) -> int:
                     break
         if not a.no_output:
             with nvtx_range("pconv:store"):
+                t0_store = _time.perf_counter()
                 eng.save_file(out_path)
+                t_store = _time.perf_counter() - t0_store
                 if rank == 0:
                     ckpt.clear_state(out_path)
         verified = None
@@ -221,6 +228,11 @@ def main(argv: list[str] | None = None) -> int:
                     "seconds": elapsed_ms / 1e3, "mpixels_per_s": mpx, "iterations": a.loops,
                     "backend": eng.backend, "filter": eng.filter.describe(), "grid": g.describe(),
                     "workers": g.workers, "plan": rep.plan, "kernel_launches": launches,
+                    "kernel_mode": (eng._impl.choose_mode(a.loops) if hasattr(eng._impl, "choose_mode") and a.loops else None),
+                    "exchange_probe_us": rep.probe or None,
+                    # whole job on this rank's clock: setup + rank-parallel read (pread overlapped with H2D) +
+                    # iterations + rank-parallel write (D2H overlapped with pwrite), everything but process start
+                    "wall_seconds": {"total": _time.perf_counter() - t_job, "load": t_load, "store": t_store},
                     "exposed_halo_wait_us": {"max": rep.max_wait_us, "sum": rep.sum_wait_us, "waits": rep.waits},
                     "halo_bytes_per_exchange_rank0": g.halo_bytes_per_iteration(0, rep.plan.get("k", 1) or 1),
                     "roofline": roof, "fraction_of_binding_roofline": round(
