@@ -142,3 +142,24 @@ def test_out_of_core_strip_plan(height, rb, loops, mem, k):
     assert 1 <= kp <= loops and (k is None or kp <= k)
     assert 1 <= S <= height
     assert S >= min(height, 2 * kp)          # a strip is at least as deep as its two halos together
+
+
+@settings(max_examples=20, deadline=None)
+@given(gy=st.integers(1, 3), gx=st.integers(1, 3), tile_h=st.integers(12, 40), tile_chunks=st.integers(2, 24),
+       c=st.sampled_from([1, 4]), k=st.integers(1, 3), R=st.sampled_from([2, 3, 4]), warps=st.sampled_from([8, 16]),
+       loops=st.integers(1, 7), seed=st.integers(0, 1000))
+def test_emulated_exchange_random_rank_grids(gy, gx, tile_h, tile_chunks, c, k, R, warps, loops, seed):
+    """Random rank grids (up to 3x3: every one of the eight directions crosses a rank boundary somewhere,
+    CTA coordinates wrap into the neighbouring rank) through the CPU replay of the pushed exchange."""
+    tile_w_px = tile_chunks * 16 // c          # tile width = whole 16-byte chunks, as the launcher requires
+    if tile_w_px < 1 or (tile_w_px * c) % 16:
+        return
+    h, w = gy * tile_h, gx * tile_w_px
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (h, w) if c == 1 else (h, w, c), dtype=np.uint8)
+    f = Filter.builtin("gaussian")
+    got = host.xplan_emulate(img, f.spec, loops, (gy, gx), k, R, warps)
+    if isinstance(got, int):
+        assert got in (-2, -4), got         # band too short for the halo / last CTA row or column too thin
+        return
+    assert np.array_equal(got, host.oracle(img, f.spec, loops))
