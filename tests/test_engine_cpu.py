@@ -51,3 +51,27 @@ def test_custom_filter_objects(rng):
     f = Filter.from_int([1, 1, 1, 1, 8, 1, 1, 1, 1], 16, name="mine")
     with ConvEngine(width=20, height=20, channels=1, filter=f, backend="cpu") as eng:
         assert np.array_equal(eng.run(img, 3), host.oracle(img, f.spec, 3))
+
+
+def test_usable_connections_follow_the_environment(monkeypatch):
+    """The package never overrides a CUDA_DEVICE_MAX_CONNECTIONS the user chose; the runtime sizes its
+    per-virtual-rank streams from what is really in effect (and falls back to streaming beyond it)."""
+    from parallel_convolution_b200.ops import cuda as K
+    monkeypatch.setenv("CUDA_DEVICE_MAX_CONNECTIONS", "1")
+    assert K.usable_connections() == 1
+    monkeypatch.setenv("CUDA_DEVICE_MAX_CONNECTIONS", "64")
+    assert K.usable_connections() == K.MAX_CONNECTIONS
+    monkeypatch.setenv("CUDA_DEVICE_MAX_CONNECTIONS", "bogus")
+    assert K.usable_connections() == 8
+    monkeypatch.delenv("CUDA_DEVICE_MAX_CONNECTIONS")
+    assert K.usable_connections() == 8
+
+
+def test_runtime_rejects_unknown_modes_and_warp_counts():
+    from parallel_convolution_b200.engine import EngineConfig
+    cfg = EngineConfig(width=64, height=48, mode="resident", warps=8)
+    assert cfg.mode == "resident" and cfg.warps == 8 and not cfg.standalone
+    import inspect
+    from parallel_convolution_b200.parallel import fused_runtime
+    src = inspect.getsource(fused_runtime.FusedRuntime.__init__)
+    assert "unknown kernel mode" in src and "8 or 16" in src
