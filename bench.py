@@ -87,6 +87,34 @@ def whole_program(exe: str, work: str, img: str, runs: int, warm: int) -> dict:
                     "100 iterations + D2H + file write"}
 
 
+def reference_mpi_rows(work: str, img: str, iters: int = 20) -> dict:
+    """The reference's CPU program on this box: unmodified ``mpi/mpi_conv.c`` (-O3) under the single-node MPI
+    stand-in (``baseline/mpi_shim``), the published tables' setting (RGB 1920x2520, 20 iterations). Its own
+    timer: iteration loop only, max over ranks (mpi/mpi_conv.c:162,250,273-283)."""
+    d = os.path.join(ROOT, "baseline", "_ref", "mpi")
+    exe, run = os.path.join(d, "mpi_conv_O3"), os.path.join(d, "mpirun_shim")
+    if not (os.path.exists(exe) and os.path.exists(run)):
+        return {"unavailable": "baseline/_ref/mpi not built (baseline/build_reference.py)"}
+    rows = {}
+    cores = os.cpu_count() or 1
+    for np_ in sorted({1, 2, 4, 8}):
+        if np_ > cores:
+            continue
+        best = None
+        for _ in range(2):
+            out = subprocess.run([run, "-np", str(np_), exe, os.path.basename(img), str(WIDTH), str(HEIGHT),
+                                  str(iters), "rgb"], cwd=work, capture_output=True, text=True, timeout=600)
+            if out.returncode != 0:
+                return {"unavailable": f"mpi_conv -np {np_} failed (rc={out.returncode}): {out.stderr[-200:]}"}
+            t = float(out.stdout.strip().splitlines()[-1])
+            best = t if best is None else min(best, t)
+        rows[f"np{np_}"] = {"seconds": round(best, 4), "mpx_s": round(WIDTH * HEIGHT * iters / best / 1e6, 1)}
+    return {"program": "baseline/_ref/mpi/mpi_conv_O3 (unmodified mpi/mpi_conv.c, gcc -O3) under baseline/mpi_shim "
+                       "(AF_UNIX stand-in for MPI; this image has no MPI installation)",
+            "iterations": iters, "host_cores": cores, "rows": rows,
+            "timer": "the program's own: iteration loop only, max over ranks"}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,12 +251,25 @@ def run_ours(a) -> dict | None:
     eng.load_synthetic(seed=4242)
     vrep = eng.iterate(LOOPS)                  # same engine, same plan, same kernels as the timed steps
     got = eng.gather()
-    verified, mismatches = True, 0
+    verified, mismatches, cpu_engine = True, 0, None
     if rank == 0:
         ref_in = HOST.synth_rect(4242, WIDTH * CHANNELS, 0, HEIGHT, 0, WIDTH * CHANNELS).reshape(HEIGHT, WIDTH, CHANNELS)
         want = HOST.cpu_run_image(ref_in, eng.filter.spec, LOOPS)
         mismatches = int((got.reshape(want.shape) != want).sum())
         verified = mismatches == 0
+        if a.gpus == 1:                        # the CPU backend on this box, the published tables' setting
+            cpu_rows = {}
+            for th in sorted({1, min(8, os.cpu_count() or 1)}):
+                best = 1e9
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    HOST.cpu_run_image(ref_in, eng.filter.spec, 20, th)
+                    best = min(best, time.perf_counter() - t0)
+                cpu_rows[f"threads{th}"] = {"seconds": round(best, 4),
+                                            "mpx_s": round(WIDTH * HEIGHT * 20 / best / 1e6, 1)}
+            cpu_engine = {"what": "native CPU engine (the mpi_conv / mpi_omp_conv analogue), RGB 1920x2520, 20 "
+                                  "iterations, one process; compare config.mpi_conv_same_box of the reference arm",
+                          "host_cores": os.cpu_count(), "rows": cpu_rows}
     probe = dict(vrep.probe) if vrep.probe else {}
     eng.close()
     if dist:
@@ -289,6 +330,7 @@ def run_ours(a) -> dict | None:
                    "timed_region": "pool->tile device copy + halo protocol + all iterations of every step",
                    "roofline_s_per_step": roof, "fraction_of_binding_roofline": round(roof_frac, 4),
                    "useful_arithmetic_fraction": useful, "exchange_probe": exchange,
+                   "cpu_engine_same_box": cpu_engine,
                    "baseline_mpx_s": BASELINE_MPX_S,
                    "baseline_source": "BASELINE.md: MPI+OMP rgb 1920x2520, 16 processes (best published RGB rate)"},
         "clocks": clocks,
@@ -366,6 +408,10 @@ def run_reference(a) -> dict:
                       "e2e_value": round(px * LOOPS / m2["t100"] / 1e6, 1), "seconds_100_iters": m2["t100"]}
         except Exception as e:  # noqa: BLE001
             row100 = {"unavailable": str(e)[:200]}
+    try:
+        mpi_rows = reference_mpi_rows(work, img)
+    except Exception as e:  # noqa: BLE001
+        mpi_rows = {"unavailable": str(e)[:200]}
     return {"metric": METRIC, "value": round(value, 1), "unit": "Mpx/s", "n_gpus": 1, "steps": K_steps,
             "warmup": W, "ms_per_step": round(m["marginal_s"] * LOOPS * 1e3, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_MPX_S, 3),
@@ -379,7 +425,8 @@ def run_reference(a) -> dict:
                                  "rate from the reference's own host timer ((t(1100 it) - t(100 it)) / 1000, best "
                                  "run each); e2e / whole_program = its whole-program time for 100 iterations incl. "
                                  "file I/O, H2D, D2H (its timer covers exactly that, cuda/main.c:20,48-50)",
-                       "rebuilt_sm_100a": row100},
+                       "rebuilt_sm_100a": row100,
+                       "mpi_conv_same_box": mpi_rows},
             "e2e": {"value": round(whole, 1), "unit": "Mpx/s", "seconds_100_iters": m["t100"],
                     "seconds_100_iters_median": m["t100_median"], "seconds_1100_iters": m["tlong"],
                     "h2d_bytes_per_step": WIDTH * HEIGHT * CHANNELS, "d2h_bytes_per_step": WIDTH * HEIGHT * CHANNELS,
