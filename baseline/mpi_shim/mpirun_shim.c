@@ -101,10 +101,17 @@ int main(int argc, char** argv) {
         int bad = !(WIFEXITED(st) && WEXITSTATUS(st) == 0);
         for (int r = 0; r < np; ++r)
             if (pid[r] == w) pid[r] = 0;
-        if (bad && !failed) {
-            failed = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + WTERMSIG(st);
-            for (int r = 0; r < np; ++r)
-                if (pid[r] > 0) kill(pid[r], SIGTERM);
+        if (bad) {
+            /* 71 = "a peer vanished under me" (mpi_shim.c): a consequence, not the cause. The status reported
+             * is the first real failure; ranks stopped by our own SIGTERM never count. */
+            const int code = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + WTERMSIG(st);
+            const int ours = WIFSIGNALED(st) && WTERMSIG(st) == SIGTERM && failed;
+            if (!failed || (failed == 71 && !ours && code != 71)) {
+                if (!failed)
+                    for (int r = 0; r < np; ++r)
+                        if (pid[r] > 0) kill(pid[r], SIGTERM);
+                failed = code;
+            }
         }
     }
     return failed;

@@ -37,7 +37,7 @@ def _pick_cxx() -> str:
 CXX = _pick_cxx()
 
 HOST_SOURCES = ["host/filters.cpp", "host/decomp.cpp", "host/cpu_engine.cpp", "host/rawio.cpp",
-                "host/planner.cpp", "host/xplan_emu.cpp"]
+                "host/planner.cpp", "host/xplan_emu.cpp", "host/shm_ranks.cpp"]
 HOST_ORACLE = "host/oracle.cpp"  # compiled separately at -O1 with contraction off
 CUDA_SOURCES = ["cuda/runtime.cu", "cuda/pack_kernels.cu", "cuda/stream_kernel.cu", "cuda/persist_kernel.cu",
                 "cuda/stream_kind_sep.cu", "cuda/stream_kind_int.cu", "cuda/stream_kind_f32.cu",
@@ -110,13 +110,22 @@ def _all_headers() -> list[Path]:
     return list(CSRC.rglob("*.h")) + list(CSRC.rglob("*.cuh"))
 
 
+def _headers(*dirs: str) -> list[Path]:
+    """Headers a target can include: its own directory plus common/ (a host-only edit must not invalidate
+    the CUDA objects, which take minutes to rebuild)."""
+    out: list[Path] = []
+    for d in dirs:
+        out += list((CSRC / d).rglob("*.h")) + list((CSRC / d).rglob("*.cuh"))
+    return out
+
+
 def build_host(force: bool = False) -> Path:
     LIB.mkdir(exist_ok=True)
     srcs = [CSRC / s for s in HOST_SOURCES] + [CSRC / HOST_ORACLE]
-    if not force and not _stale(HOST_LIB, srcs + _all_headers(), CXXFLAGS):
+    if not force and not _stale(HOST_LIB, srcs + _headers("host", "common"), CXXFLAGS):
         return HOST_LIB
     with _BuildLock():
-        if not force and not _stale(HOST_LIB, srcs + _all_headers(), CXXFLAGS):
+        if not force and not _stale(HOST_LIB, srcs + _headers("host", "common"), CXXFLAGS):
             return HOST_LIB      # another rank built it while we waited for the lock
         return _build_host_locked(srcs)
 
@@ -132,7 +141,7 @@ def _build_host_locked(srcs: list[Path]) -> Path:
           "-c", str(CSRC / HOST_ORACLE), "-o", str(o)])
     objs.append(str(o))
     _link([CXX, "-shared", "-fopenmp"], HOST_LIB, objs, [])
-    _stamp(HOST_LIB, srcs + _all_headers(), CXXFLAGS)
+    _stamp(HOST_LIB, srcs + _headers("host", "common"), CXXFLAGS)
     return HOST_LIB
 
 
@@ -150,10 +159,10 @@ def build_host_sanitized() -> Path:
 def build_cuda(force: bool = False) -> Path:
     LIB.mkdir(exist_ok=True)
     srcs = [CSRC / s for s in CUDA_SOURCES if (CSRC / s).exists()]
-    if not force and not _stale(CUDA_LIB, srcs + _all_headers(), NVCCFLAGS):
+    if not force and not _stale(CUDA_LIB, srcs + _headers("cuda", "common"), NVCCFLAGS):
         return CUDA_LIB
     with _BuildLock():
-        if not force and not _stale(CUDA_LIB, srcs + _all_headers(), NVCCFLAGS):
+        if not force and not _stale(CUDA_LIB, srcs + _headers("cuda", "common"), NVCCFLAGS):
             return CUDA_LIB
         return _build_cuda_locked(srcs, force)
 
@@ -162,7 +171,7 @@ def _build_cuda_locked(srcs: list[Path], force: bool) -> Path:
     if not Path(NVCC).exists():
         raise RuntimeError(f"nvcc not found at {NVCC}; the CUDA library cannot be built")
     from concurrent.futures import ThreadPoolExecutor
-    hdrs = _all_headers()
+    hdrs = _headers("cuda", "common")
 
     def compile_one(s: Path) -> str:
         o = LIB / (s.stem + ".cu.o")
@@ -175,7 +184,7 @@ def _build_cuda_locked(srcs: list[Path], force: bool) -> Path:
         objs = list(ex.map(compile_one, srcs))
     _link([NVCC, "-ccbin", CXX, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"], CUDA_LIB, objs,
           ["-lcudart_static", "-lpthread", "-ldl", "-lrt"])
-    _stamp(CUDA_LIB, srcs + _all_headers(), NVCCFLAGS)
+    _stamp(CUDA_LIB, srcs + _headers("cuda", "common"), NVCCFLAGS)
     return CUDA_LIB
 
 

@@ -8,7 +8,9 @@ Reference grammar (``mpi/mpi_conv.c:340-360``, ``cuda/funcs.c:10-29``), kept ver
   (the reference's ``./cuda_conv ...``; add ``--backend cpu`` for a GPU-less box)
 * one process per GPU:       ``torchrun --standalone --local-addr 127.0.0.1 --nproc-per-node 8 -m
   parallel_convolution_b200 img.raw 1920 2520 50 rgb`` (the reference's ``mpirun -np 8 ./mpi_conv``)
-* CPU ranks over gloo:       same with ``--backend cpu`` (``mpi_conv`` / ``mpi_omp_conv --threads T``)
+* CPU ranks:                 same with ``--backend cpu`` (``mpi_conv`` / ``mpi_omp_conv --threads T``); ranks of one
+                             node share the image in /dev/shm and trade no messages (``--cpu-transport shm``),
+                             ranks of several nodes exchange gloo messages
 
 Output: ``blur_<basename>`` next to the input (``-o`` overrides) and the elapsed seconds of the
 iteration loop on stdout, max over ranks (``mpi/mpi_conv.c:273-283`` prints ``%f\\n``); ``--json``
@@ -59,6 +61,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--autotune", action="store_true",
                    help="fused backend: measure candidate launch plans on this machine before the run")
     p.add_argument("--threads", type=int, default=0, help="cpu backend: OpenMP threads per rank")
+    p.add_argument("--cpu-transport", default="auto", choices=["auto", "shm", "gloo"],
+                   help="cpu backend with several ranks: halos through a shared image in /dev/shm (one node; "
+                        "auto picks it when possible) or as gloo messages")
     p.add_argument("--out-of-core", type=int, default=None, metavar="MiB",
                    help="cpu backend, single process: stream the file through row strips with k-deep halos, "
                         "holding at most ~MiB of the image in memory (images larger than RAM)")
@@ -160,7 +165,8 @@ def main(argv: list[str] | None = None) -> int:
         with nvtx_range("pconv:setup"):
             eng = ConvEngine(width=a.width, height=a.height, channels=channels, filter=a.filter,
                              backend=a.backend, workers=a.workers, grid=grid, halo_depth=a.halo_depth,
-                             mode=a.mode, warps=a.warps or None, threads=a.threads, timeout_ms=a.timeout_ms,
+                             mode=a.mode, warps=a.warps or None, threads=a.threads, cpu_transport=a.cpu_transport,
+                             timeout_ms=a.timeout_ms,
                              slots=3 if a.batch else 1)
         if a.inject_drop_signal is not None and hasattr(eng._impl, "drivers"):
             for r, d in eng._impl.drivers.items():

@@ -120,10 +120,56 @@ extern "C" int pconv_cpu_convolve(const uint8_t* src0, uint8_t* dst0, int64_t pi
 }
 
 // Temporal blocking on the CPU (the same idea as the GPU kernels, one level up the hierarchy): a
-// thread takes a band of rows plus a k-row halo into L2-sized private ping-pong buffers, advances it
-// k iterations there (the halo absorbs the staleness; rows on the image border keep their zero
-// padding and never go stale), and writes the band back — two passes over memory per k iterations
+// thread takes a band of rows plus a k-deep halo into cache-sized private ping-pong buffers, advances it
+// k iterations there (the halo absorbs the staleness; rows and columns on the image border keep their
+// zero padding and never go stale), and writes the band back — two passes over memory per k iterations
 // instead of 2k. Exactly the oracle's arithmetic, so the result is bit-identical.
+
+extern "C" int64_t pconv_cpu_band_scratch_bytes(int64_t band_rows, int64_t cols, int C, int k) {
+    const int64_t lpitch = ((cols + 2 * k + 2) * C + 63) / 64 * 64;
+    return (band_rows + 2 * k + 2) * lpitch;
+}
+
+// One band: rows [r0,r1) x pixel columns [c0,c1) of an H x W image advance kk iterations. src0/dst0 point
+// at pixel (0,0) of two images with the same pitch and a valid zero frame; the band's halo is read from src
+// (it may belong to other bands, threads or ranks), only the band itself is written to dst. xa/xb: two
+// scratch buffers of pconv_cpu_band_scratch_bytes(r1 - r0, c1 - c0, C, kk) bytes each.
+extern "C" void pconv_cpu_band_advance(const uint8_t* src0, uint8_t* dst0, int64_t pitch, int64_t H, int64_t W,
+                                       int C, const pconv_filter_t* f, int64_t r0, int64_t r1, int64_t c0,
+                                       int64_t c1, int kk, uint8_t* sa, uint8_t* sb) {
+    if (kk == 1) {   // nothing to block: straight from image to image, the halo is read in place
+        for (int64_t y = r0; y < r1; ++y) one_row(src0, dst0, pitch, C, f, y, c0, c1);
+        return;
+    }
+    const int64_t lo = std::max<int64_t>(0, r0 - kk), hi = std::min(H, r1 + kk);
+    const int64_t bl = std::max<int64_t>(0, c0 - kk), bh = std::min(W, c1 + kk);
+    const int64_t rows = hi - lo, cols = bh - bl;
+    const int64_t lpitch = ((c1 - c0 + 2 * kk + 2) * C + 63) / 64 * 64;
+    uint8_t* xa = sa + lpitch + C;    // local pixel (0,0) == image pixel (lo, bl)
+    uint8_t* xb = sb + lpitch + C;
+    // 1-pixel frame = the zero padding wherever the band touches the image border; at cut edges the frame is
+    // only read by outputs that are discarded (the valid region shrinks by one per iteration)
+    for (uint8_t* x : {xa, xb}) {
+        std::memset(x - lpitch - C, 0, (size_t)((cols + 2) * C));
+        std::memset(x + rows * lpitch - C, 0, (size_t)((cols + 2) * C));
+        for (int64_t y = 0; y < rows; ++y) {
+            std::memset(x + y * lpitch - C, 0, (size_t)C);
+            std::memset(x + y * lpitch + cols * C, 0, (size_t)C);
+        }
+    }
+    for (int64_t y = 0; y < rows; ++y)
+        std::memcpy(xa + y * lpitch, src0 + (lo + y) * pitch + bl * C, (size_t)(cols * C));
+    for (int j = 1; j <= kk; ++j) {
+        // still exact after j iterations: j away from a cut edge, all the way to an image edge
+        const int64_t ra = lo > 0 ? j : 0, re = hi < H ? rows - j : rows;
+        const int64_t ca = bl > 0 ? j : 0, ce = bh < W ? cols - j : cols;
+        for (int64_t y = ra; y < re; ++y) one_row(xa, xb, lpitch, C, f, y, ca, ce);
+        std::swap(xa, xb);
+    }
+    for (int64_t y = r0; y < r1; ++y)
+        std::memcpy(dst0 + y * pitch + c0 * C, xa + (y - lo) * lpitch + (c0 - bl) * C, (size_t)((c1 - c0) * C));
+}
+
 static int run_image_blocked(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
                              const pconv_filter_t* f, int loops, int threads, int k) {
     const int64_t rb = W * (int64_t)C;
@@ -138,35 +184,26 @@ static int run_image_blocked(const uint8_t* src, uint8_t* dst, int64_t H, int64_
     band = std::max<int64_t>(band, 8);
     band = std::min<int64_t>(band, std::max<int64_t>((H + nt - 1) / nt, 8));
     const int64_t nbands = (H + band - 1) / band;
-    for (int done = 0; done < loops;) {
-        const int kk = std::min(k, loops - done);
-#pragma omp parallel num_threads(nt)
-        {
-            std::vector<uint8_t> la, lb;
+    const size_t sbytes = (size_t)pconv_cpu_band_scratch_bytes(band, W, C, k);
+    std::vector<std::vector<uint8_t>> scratch((size_t)nt * 2);   // allocated once: no malloc in the passes
+#pragma omp parallel num_threads(nt) if (nt > 1)
+    {
+        const int tid = omp_get_thread_num();
+        scratch[(size_t)tid * 2].assign(sbytes, 0);
+        scratch[(size_t)tid * 2 + 1].assign(sbytes, 0);
+        for (int done = 0; done < loops;) {
+            const int kk = std::min(k, loops - done);
+            const uint8_t* from = (done / k) & 1 ? pb : pa;
+            uint8_t* to = (done / k) & 1 ? pa : pb;
 #pragma omp for schedule(dynamic)
-            for (int64_t b = 0; b < nbands; ++b) {
-                const int64_t r0 = b * band, r1 = std::min(H, r0 + band);
-                const int64_t lo = std::max<int64_t>(0, r0 - kk), hi = std::min(H, r1 + kk);
-                const int64_t rows = hi - lo;
-                la.assign((size_t)((rows + 2) * pitch), 0);
-                lb.assign((size_t)((rows + 2) * pitch), 0);
-                uint8_t* xa = la.data() + pitch + C;   // local pixel (0,0) == image row lo
-                uint8_t* xb = lb.data() + pitch + C;
-                for (int64_t y = 0; y < rows; ++y) std::memcpy(xa + y * pitch, pa + (lo + y) * pitch, (size_t)rb);
-                for (int j = 1; j <= kk; ++j) {
-                    // rows still exact after j iterations: j away from a cut edge, all the way to an
-                    // image edge (zero padding is always valid)
-                    const int64_t a = lo > 0 ? j : 0, e = hi < H ? rows - j : rows;
-                    for (int64_t y = a; y < e; ++y) one_row(xa, xb, pitch, C, f, y, 0, W);
-                    std::swap(xa, xb);
-                }
-                for (int64_t y = r0; y < r1; ++y) std::memcpy(pb + y * pitch, xa + (y - lo) * pitch, (size_t)rb);
-            }
+            for (int64_t b = 0; b < nbands; ++b)
+                pconv_cpu_band_advance(from, to, pitch, H, W, C, f, b * band, std::min(H, b * band + band), 0, W,
+                                       kk, scratch[(size_t)tid * 2].data(), scratch[(size_t)tid * 2 + 1].data());
+            done += kk;      // the implicit barrier of the loop separates the passes
         }
-        std::swap(pa, pb);
-        done += kk;
     }
-    for (int64_t y = 0; y < H; ++y) std::memcpy(dst + y * rb, pa + y * pitch, (size_t)rb);
+    const uint8_t* last = ((loops + k - 1) / k) & 1 ? pb : pa;
+    for (int64_t y = 0; y < H; ++y) std::memcpy(dst + y * rb, last + y * pitch, (size_t)rb);
     return 0;
 }
 

@@ -74,12 +74,43 @@ int pconv_cpu_run_image(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, 
 // (pconv_cpu_run_image picks this automatically for memory-bound sizes).
 int pconv_cpu_run_image_blocked(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
                                 const pconv_filter_t* f, int loops, int threads, int k);
+// The building block of every temporally blocked CPU path: rows [r0,r1) x pixel columns [c0,c1) of an
+// H x W image advance kk iterations inside two scratch buffers (each pconv_cpu_band_scratch_bytes(r1-r0,
+// c1-c0, C, kk) bytes); the kk-deep halo is read from src0, only the band itself is written to dst0. Both
+// images share `pitch` and carry a zero frame; src0/dst0 point at pixel (0,0).
+int64_t pconv_cpu_band_scratch_bytes(int64_t band_rows, int64_t cols, int C, int k);
+void pconv_cpu_band_advance(const uint8_t* src0, uint8_t* dst0, int64_t pitch, int64_t H, int64_t W, int C,
+                            const pconv_filter_t* f, int64_t r0, int64_t r1, int64_t c0, int64_t c1, int kk,
+                            uint8_t* scratch_a, uint8_t* scratch_b);
 // Out-of-core: file -> file, `loops` iterations, never holding more than ~mem_bytes of the image
 // (row strips with k-deep halos, ceil(loops/k) passes; intermediate passes use "<out>.pass").
 // k <= 0 / mem_bytes <= 0 pick defaults (8 iterations per pass, 256 MiB). 0 or -errno.
 int pconv_cpu_run_file(const char* in_path, const char* out_path, int64_t H, int64_t W, int C,
                        const pconv_filter_t* f, int loops, int threads, int k, int64_t mem_bytes);
 int pconv_omp_max_threads(void);
+
+// ---- CPU ranks of one node over a shared image (csrc/host/shm_ranks.cpp) -------------------------
+// One segment (a file under /dev/shm) holds both ping-pong images, zero frame included, and one epoch
+// counter per rank; ranks read their halos directly from the neighbours' part of the image.
+typedef struct pconv_shm pconv_shm_t;
+// Rank 0 creates (fails if the path exists), the others attach after it; NULL on error. The path may be
+// unlinked as soon as every rank has attached.
+pconv_shm_t* pconv_shm_create(const char* path, int64_t H, int64_t W, int C, int nranks);
+pconv_shm_t* pconv_shm_attach(const char* path);
+void pconv_shm_close(pconv_shm_t* s);
+uint8_t* pconv_shm_pixels(pconv_shm_t* s, int which);   // pixel (0,0) of image 0 / 1
+int64_t pconv_shm_pitch(const pconv_shm_t* s);
+int64_t pconv_shm_bytes(const pconv_shm_t* s);
+int64_t pconv_shm_epoch(const pconv_shm_t* s, int rank);   // epochs completed; newest data in image[epoch & 1]
+void pconv_shm_reset(pconv_shm_t* s, int rank);           // epoch := 0 (callers synchronise around it)
+void pconv_shm_abort(pconv_shm_t* s, int rank);           // make ranks waiting on `rank` fail with -ECANCELED
+// Advance this rank's tile (rows [r0,r1), pixel columns [c0,c1)) by `loops` iterations, k per epoch.
+// nbr[9]: neighbour ranks in row-major 3x3 order (index 4 = self), -1 where the image ends; k must not
+// exceed the smallest neighbouring tile extent. 0, -EINVAL, -ETIMEDOUT (a neighbour did not advance within
+// timeout_s; <= 0 waits forever) or -ECANCELED (a neighbour aborted).
+int pconv_shm_run(pconv_shm_t* s, int rank, int64_t r0, int64_t r1, int64_t c0, int64_t c1,
+                  const int32_t nbr[9], const pconv_filter_t* f, int loops, int k, int threads,
+                  double timeout_s, int64_t* epochs_run);
 
 // ---- raw image I/O (64-bit offsets; reference: MPI_File_* mpi/mpi_conv.c:133-147,253-271) ----
 int64_t pconv_file_size(const char* path);

@@ -43,6 +43,7 @@ class EngineConfig:
     mode: str = "auto"               # fused backend: auto | stream | resident (persistent kernel)
     warps: int | None = None         # persistent kernel: warps per CTA (8 | 16; None: planner/autotuner)
     threads: int = 0                 # cpu backend: OpenMP threads per rank
+    cpu_transport: str = "auto"      # cpu backend, several ranks: auto | shm (shared image, one node) | gloo (messages)
     device: int | None = None        # CUDA device index (default: LOCAL_RANK or 0)
     timeout_ms: float = 10_000.0     # in-kernel watchdog for neighbour flags
     slots: int = 1                   # buffer sets for pipelined streaming steps (H2D || iterate || D2H)
@@ -123,9 +124,31 @@ class ConvEngine:
                 raise RuntimeError(f"backend {want!r} needs a CUDA device and libpconv_cuda.so")
         return want
 
+    def _pick_cpu_transport(self, want: str) -> str:
+        """How CPU ranks trade halos: through a shared image when they all sit on one node (no messages, see
+        parallel/shm_backend.py), as gloo messages otherwise (the reference's MPI schedule)."""
+        want = os.environ.get("PCONV_CPU_TRANSPORT", want or "auto")
+        if want not in ("auto", "shm", "gloo"):
+            raise ValueError(f"unknown cpu transport {want!r}")
+        if not self.distributed:
+            return "local"
+        if want == "gloo":
+            return "gloo"
+        from .parallel.shm_backend import same_node
+        ok = same_node(self.dist)                 # collective: every rank takes the same branch
+        if want == "shm" and not ok:
+            raise RuntimeError("cpu transport 'shm' needs every rank on one node with /dev/shm")
+        return "shm" if ok else "gloo"
+
     def _setup(self) -> None:
         cfg = self.cfg
         if self.backend == "cpu":
+            self.cpu_transport = self._pick_cpu_transport(cfg.cpu_transport)
+            if self.cpu_transport == "shm":
+                from .parallel.shm_backend import ShmTile
+                self._impl = ShmTile(self.grid, self.rank, self.filter, cfg.halo_depth, cfg.threads, self.dist,
+                                     timeout_ms=cfg.timeout_ms)
+                return
             from .parallel.host_backend import HostTile
             k = cfg.halo_depth or 1
             self._impl = HostTile(self.grid, self.rank if self.distributed else 0, self.filter, k,
@@ -302,7 +325,8 @@ class ConvEngine:
             ms = (time.perf_counter() - t0) * 1e3
             rep.elapsed_ms = self._max_over_ranks(ms)
             rep.launches = 0
-            rep.plan = {"k": self._impl.k, "exchanges": self._impl.exchanges}
+            rep.plan = {"k": self._impl.k, "exchanges": self._impl.exchanges,
+                        "transport": getattr(self, "cpu_transport", "local")}
         else:
             self._impl.run(loops, rep, sync=sync)
             if sync:

@@ -73,6 +73,24 @@ def lib() -> C.CDLL:
     L.pconv_synth_rect.restype = None
     L.pconv_host_version.restype = C.c_char_p
     L.pconv_plan.argtypes = [C.POINTER(PlanRequest), C.POINTER(PlanResult)]
+    L.pconv_shm_create.argtypes = [C.c_char_p, i64, i64, C.c_int, C.c_int]
+    L.pconv_shm_create.restype = C.c_void_p
+    L.pconv_shm_attach.argtypes = [C.c_char_p]
+    L.pconv_shm_attach.restype = C.c_void_p
+    L.pconv_shm_close.argtypes = [C.c_void_p]
+    L.pconv_shm_close.restype = None
+    L.pconv_shm_pixels.argtypes = [C.c_void_p, C.c_int]
+    L.pconv_shm_pixels.restype = C.c_void_p
+    for fn in (L.pconv_shm_pitch, L.pconv_shm_bytes):
+        fn.argtypes = [C.c_void_p]
+        fn.restype = i64
+    L.pconv_shm_epoch.argtypes = [C.c_void_p, C.c_int]
+    L.pconv_shm_epoch.restype = i64
+    for fn in (L.pconv_shm_reset, L.pconv_shm_abort):
+        fn.argtypes = [C.c_void_p, C.c_int]
+        fn.restype = None
+    L.pconv_shm_run.argtypes = [C.c_void_p, C.c_int, i64, i64, i64, i64, C.POINTER(C.c_int32), fsp, C.c_int,
+                                C.c_int, C.c_int, C.c_double, C.POINTER(i64)]
     return L
 
 
@@ -192,6 +210,62 @@ def cpu_run_file(path_in: str, path_out: str, height: int, width: int, Cn: int, 
     if rc != 0:
         raise OSError(-rc if rc < 0 else rc, f"out-of-core run failed ({os.strerror(-rc) if rc < 0 else rc}): "
                                              f"{path_in} -> {path_out}")
+
+
+class ShmSegment:
+    """The shared image of the CPU ranks of one node (csrc/host/shm_ranks.cpp): two ping-pong images with
+    their zero frame and one epoch counter per rank. Rank 0 creates it, the others attach."""
+
+    def __init__(self, path: str, height: int = 0, width: int = 0, Cn: int = 0, nranks: int = 0,
+                 create: bool = False):
+        L = lib()
+        self.path, self._h = path, None
+        h = (L.pconv_shm_create(os.fsencode(path), height, width, Cn, nranks) if create
+             else L.pconv_shm_attach(os.fsencode(path)))
+        if not h:
+            raise OSError(f"cannot {'create' if create else 'attach to'} shared segment {path}")
+        self._h = h
+        self.pitch = int(L.pconv_shm_pitch(h))
+        self.nbytes = int(L.pconv_shm_bytes(h))
+
+    def image(self, which: int, height: int, row_bytes: int) -> np.ndarray:
+        """Writable (height, row_bytes) view of image ``which`` (0/1), frame excluded."""
+        base = lib().pconv_shm_pixels(self._h, which & 1)
+        buf = (C.c_uint8 * ((height - 1) * self.pitch + row_bytes)).from_address(base)
+        flat = np.frombuffer(buf, dtype=np.uint8)
+        return np.lib.stride_tricks.as_strided(flat, shape=(height, row_bytes), strides=(self.pitch, 1))
+
+    def epoch(self, rank: int) -> int:
+        return int(lib().pconv_shm_epoch(self._h, rank))
+
+    def reset(self, rank: int) -> None:
+        lib().pconv_shm_reset(self._h, rank)
+
+    def abort(self, rank: int) -> None:
+        lib().pconv_shm_abort(self._h, rank)
+
+    def run(self, rank: int, rect: tuple[int, int, int, int], nbr: list[int], f: FilterSpec, loops: int, k: int,
+            threads: int = 1, timeout_s: float = 0.0) -> int:
+        """Advance ``rank``'s tile ``rect`` = (r0, r1, c0, c1) by ``loops`` iterations; returns the epochs run."""
+        arr = (C.c_int32 * 9)(*[int(v) for v in nbr])
+        ran = C.c_int64(0)
+        rc = lib().pconv_shm_run(self._h, rank, *[int(v) for v in rect], arr, C.byref(f), loops, k,
+                                 max(1, int(threads)), float(timeout_s), C.byref(ran))
+        if rc != 0:
+            raise OSError(-rc, f"shared-memory rank {rank}: {os.strerror(-rc)} "
+                               f"({'a neighbour stopped advancing' if rc == -110 else 'a neighbour gave up' if rc == -125 else 'bad arguments'})")
+        return int(ran.value)
+
+    def close(self) -> None:
+        if self._h:
+            lib().pconv_shm_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def cpu_convolve(src: np.ndarray, dst: np.ndarray, halo: int, Cn: int, f: FilterSpec,

@@ -1,5 +1,5 @@
 """Multi-process CPU tests (gloo, world_size > 1, no GPU): the host backend's 8-neighbour halo
-exchange and the CLI under torchrun. These are the tests the reference's own np>1 runs would fail
+exchange — as gloo messages and through the shared image of one node — and the CLI under torchrun. These are the tests the reference's own np>1 runs would fail
 (diagonal cells never exchanged, corner pixels never recomputed: defects D1/D2)."""
 import os
 import socket
@@ -25,14 +25,15 @@ def _torchrun(nproc: int, args: list[str], timeout: int = 240, **extra_env) -> s
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
 
 
+@pytest.mark.parametrize("transport", ["gloo", "shm"])
 @pytest.mark.parametrize("nproc,extra", [
     (2, []),
     (4, ["--halo-depth", "3", "--filter", "sharpen"]),          # 2x2: exercises the diagonal cells
     (6, ["--filter", "box", "--height", "90", "--width", "131"]),  # remainder tiles
 ])
-def test_host_backend_matches_single_process(nproc, extra):
+def test_host_backend_matches_single_process(nproc, extra, transport):
     r = _torchrun(nproc, [os.path.join(ROOT, "scripts", "dist_check.py"), "--backend", "cpu",
-                          "--height", "96", "--width", "120"] + extra)
+                          "--height", "96", "--width", "120"] + extra, PCONV_CPU_TRANSPORT=transport)
     assert "DIST_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
@@ -41,7 +42,8 @@ def test_poisoned_halos_are_always_refreshed(depth):
     """PCONV_POISON_HALO=1 overwrites every neighbour-facing halo with 0xA5 before each exchange: the
     result stays exact only if all eight strips (diagonals included) are freshly received each time."""
     r = _torchrun(4, [os.path.join(ROOT, "scripts", "dist_check.py"), "--backend", "cpu", "--height", "66",
-                      "--width", "70", "--loops", "7", "--halo-depth", str(depth)], PCONV_POISON_HALO="1")
+                      "--width", "70", "--loops", "7", "--halo-depth", str(depth)], PCONV_POISON_HALO="1",
+                  PCONV_CPU_TRANSPORT="gloo")
     assert "DIST_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
