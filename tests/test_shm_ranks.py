@@ -74,6 +74,8 @@ def _gather(tiles, h, rb, c):
     (37, 29, 1, 1, None, "gaussian", 9, 4, 3, 1),        # one rank, more threads than bands
 ])
 def test_thread_ranks_match_the_oracle(h, w, c, workers, grid, filt, loops, k, threads, calls):
+    if os.environ.get("PCONV_TEST_SINGLE_THREAD_RANKS"):
+        threads = 1      # ThreadSanitizer run (scripts/host_sanitize.sh): libgomp's barriers are not instrumented
     g, f, seg, tiles = _ranks(h, w, c, workers, grid, filt, k, threads)
     shape = (h, w) if c == 1 else (h, w, c)
     img = np.random.default_rng(h * w + workers).integers(0, 256, shape, dtype=np.uint8)
