@@ -259,12 +259,17 @@ def run_ours(a) -> dict | None:
         verified = mismatches == 0
         if a.gpus == 1:                        # the CPU backend on this box, the published tables' setting
             cpu_rows = {}
+            from parallel_convolution_b200 import ConvEngine as _CpuEngine
             for th in sorted({1, min(8, os.cpu_count() or 1)}):
+                ce = _CpuEngine(width=WIDTH, height=HEIGHT, channels=CHANNELS, filter=eng.filter, backend="cpu",
+                                threads=th, standalone=True)
                 best = 1e9
                 for _ in range(3):
-                    t0 = time.perf_counter()
-                    HOST.cpu_run_image(ref_in, eng.filter.spec, 20, th)
+                    ce.load_image(ref_in)
+                    t0 = time.perf_counter()               # the iteration loop only, like the reference's MPI timer
+                    ce._impl.iterate(20)
                     best = min(best, time.perf_counter() - t0)
+                ce.close()
                 cpu_rows[f"threads{th}"] = {"seconds": round(best, 4),
                                             "mpx_s": round(WIDTH * HEIGHT * 20 / best / 1e6, 1)}
             cpu_engine = {"what": "native CPU engine (the mpi_conv / mpi_omp_conv analogue), RGB 1920x2520, 20 "
@@ -308,6 +313,26 @@ def run_ours(a) -> dict | None:
             whole = whole_program(str(B.NATIVE_BIN), work, img, runs=max(3, min(K_steps, 10)), warm=2)
         except Exception as e:  # noqa: BLE001
             whole = {"unavailable": str(e)[:200]}
+        try:                                   # `pconv_native -np N --cpu` == `mpirun -np N ./mpi_conv` (20 iterations)
+            if cpu_engine is not None:
+                for np_ in (2, 4, 8):
+                    if np_ > (os.cpu_count() or 1):
+                        continue
+                    best = 1e9
+                    for _ in range(3):
+                        out = subprocess.run([str(B.NATIVE_BIN), "-np", str(np_), os.path.basename(img), str(WIDTH),
+                                              str(HEIGHT), "20", "rgb", "--cpu", "-o", "ranks_out.raw"], cwd=work,
+                                             capture_output=True, text=True, timeout=300)
+                        if out.returncode != 0:
+                            raise RuntimeError(out.stderr[-200:])
+                        best = min(best, float(out.stdout.strip().splitlines()[-1]))
+                    cpu_engine["rows"][f"ranks{np_}"] = {"seconds": round(best, 4),
+                                                         "mpx_s": round(WIDTH * HEIGHT * 20 / best / 1e6, 1)}
+                cpu_engine["ranks"] = ("pconv_native -np N --cpu: N forked processes over one shared image "
+                                       "(csrc/host/shm_ranks.cpp), loop time, max over ranks")
+        except Exception as e:  # noqa: BLE001
+            if cpu_engine is not None:
+                cpu_engine["ranks"] = f"unavailable: {str(e)[:160]}"
     if not verified:
         print(json.dumps({"impl": "ours", "error": f"verification failed: {mismatches} bytes differ from the CPU engine",
                           "n_gpus": a.gpus}), flush=True)

@@ -104,6 +104,11 @@ int64_t pconv_shm_bytes(const pconv_shm_t* s);
 int64_t pconv_shm_epoch(const pconv_shm_t* s, int rank);   // epochs completed; newest data in image[epoch & 1]
 void pconv_shm_reset(pconv_shm_t* s, int rank);           // epoch := 0 (callers synchronise around it)
 void pconv_shm_abort(pconv_shm_t* s, int rank);           // make ranks waiting on `rank` fail with -ECANCELED
+// For launchers without a process group (pconv_native -np N; the mapping survives fork()): a barrier over the
+// segment's nranks processes (0, -ETIMEDOUT, -ECANCELED when a rank aborted) and one double per rank.
+int pconv_shm_barrier(pconv_shm_t* s, double timeout_s);
+void pconv_shm_set_value(pconv_shm_t* s, int rank, double v);
+double pconv_shm_get_value(const pconv_shm_t* s, int rank);
 // Advance this rank's tile (rows [r0,r1), pixel columns [c0,c1)) by `loops` iterations, k per epoch.
 // nbr[9]: neighbour ranks in row-major 3x3 order (index 4 = self), -1 where the image ends; k must not
 // exceed the smallest neighbouring tile extent. 0, -EINVAL, -ETIMEDOUT (a neighbour did not advance within

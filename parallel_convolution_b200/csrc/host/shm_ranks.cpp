@@ -52,7 +52,14 @@ struct Header {
 struct alignas(64) Counter {
     std::atomic<int64_t> done;     // epochs completed since the last reset
     std::atomic<int32_t> abort;    // set when this rank gave up: waiters stop waiting
+    double value;                  // a number the rank leaves for whoever collects results (its loop time)
 };
+
+// Process barrier for launchers that have no process group (pconv_native -np N): central counter + generation.
+struct alignas(64) Barrier {
+    std::atomic<int64_t> count, gen;
+};
+constexpr int64_t kBarrierOffset = 2048;   // inside the header page, after the Header fields
 static_assert(sizeof(Counter) == 64, "one cache line per rank");
 static_assert(std::atomic<int64_t>::is_always_lock_free, "counters live in shared memory");
 
@@ -71,7 +78,9 @@ struct pconv_shm {
     uint8_t* base;
     Header* h;
     Counter* ctr;
+    Barrier* bar() const { return (Barrier*)(base + kBarrierOffset); }
 };
+static_assert(sizeof(Header) <= kBarrierOffset, "the barrier sits behind the header");
 
 namespace {
 
@@ -152,7 +161,11 @@ extern "C" pconv_shm_t* pconv_shm_create(const char* path, int64_t H, int64_t W,
         new (&s->ctr[r]) Counter;
         s->ctr[r].done.store(0, std::memory_order_relaxed);
         s->ctr[r].abort.store(0, std::memory_order_relaxed);
+        s->ctr[r].value = 0.0;
     }
+    new (s->bar()) Barrier;
+    s->bar()->count.store(0, std::memory_order_relaxed);
+    s->bar()->gen.store(0, std::memory_order_relaxed);
     std::atomic_thread_fence(std::memory_order_release);
     return s;
 }
@@ -206,6 +219,39 @@ extern "C" void pconv_shm_reset(pconv_shm_t* s, int rank) {
     if (!s || rank < 0 || rank >= s->h->nranks) return;
     s->ctr[rank].abort.store(0, std::memory_order_relaxed);
     s->ctr[rank].done.store(0, std::memory_order_release);
+}
+
+extern "C" int pconv_shm_barrier(pconv_shm_t* s, double timeout_s) {
+    if (!s) return -EINVAL;
+    Barrier* b = s->bar();
+    const int64_t gen = b->gen.load(std::memory_order_acquire);
+    if (b->count.fetch_add(1, std::memory_order_acq_rel) + 1 == s->h->nranks) {
+        b->count.store(0, std::memory_order_relaxed);
+        b->gen.store(gen + 1, std::memory_order_release);
+        return 0;
+    }
+    double t0 = 0.0;
+    for (uint32_t spin = 0; b->gen.load(std::memory_order_acquire) == gen; ++spin) {
+        if (spin < 1024) {
+            sched_yield();
+        } else {
+            if (t0 == 0.0) t0 = now_s();
+            if (timeout_s > 0 && now_s() - t0 > timeout_s) return -ETIMEDOUT;
+            for (int r = 0; r < s->h->nranks; ++r)
+                if (s->ctr[r].abort.load(std::memory_order_relaxed)) return -ECANCELED;
+            timespec nap = {0, 100000};
+            nanosleep(&nap, nullptr);
+        }
+    }
+    return 0;
+}
+
+extern "C" void pconv_shm_set_value(pconv_shm_t* s, int rank, double v) {
+    if (s && rank >= 0 && rank < s->h->nranks) s->ctr[rank].value = v;
+}
+
+extern "C" double pconv_shm_get_value(const pconv_shm_t* s, int rank) {
+    return (s && rank >= 0 && rank < s->h->nranks) ? s->ctr[rank].value : 0.0;
 }
 
 extern "C" void pconv_shm_abort(pconv_shm_t* s, int rank) {

@@ -1,13 +1,22 @@
 // pconv_native — stand-alone native CLI (no Python): the drop-in for the reference's ./cuda_conv
 // (cuda/main.c:10-55) on one B200, with a native CPU fallback (--cpu) for GPU-less boxes.
 //
-//   pconv_native image width height loops {rgb|grey} [--filter NAME] [--cpu] [--threads T]
-//                [--out-of-core MiB] [-o OUT]
+//   pconv_native [-np N] image width height loops {rgb|grey} [--filter NAME] [--cpu] [--threads T]
+//                [--halo-depth K] [--out-of-core MiB] [-o OUT]
+//
+// `-np N` (with --cpu, or on a box without a GPU) is `mpirun -np N ./mpi_conv ...` (mpi/READ_ME.txt:4-5) without
+// MPI and without Python: N processes forked over one shared image (host/shm_ranks.cpp), every rank reads its
+// tile rows from the file, iterates, and writes them back (the reference's MPI_File_* pattern,
+// mpi/mpi_conv.c:133-147,253-271); the time printed is the iteration loop, max over ranks.
 //
 // Same positional grammar and the same "Execution time: %.3f sec" line (whole program: file read,
 // H2D, kernels, D2H, file write — cuda/main.c:20,48-50), plus the loop-only seconds on a second
 // line. Everything is the same native code the Python package drives: raw I/O, filter
 // classification and launch planning from libpconv_host.so, kernels from libpconv_cuda.so.
+#include <signal.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -29,8 +38,8 @@ const Builtin kBuiltins[] = {
 };
 
 int usage(const char* prog) {
-    std::fprintf(stderr, "Error Input!\n%s image_name width height loops [rgb/grey] "
-                         "[--filter NAME] [--cpu] [--threads T] [--out-of-core MiB] [-o OUT]\n", prog);
+    std::fprintf(stderr, "Error Input!\n%s [-np N] image_name width height loops [rgb/grey] "
+                         "[--filter NAME] [--cpu] [--threads T] [--halo-depth K] [--out-of-core MiB] [-o OUT]\n", prog);
     return EXIT_FAILURE;
 }
 
@@ -46,9 +55,99 @@ double now_s() {
         }                                                                             \
     } while (0)
 
+// N CPU ranks over one shared image. Returns the process exit code.
+int run_cpu_ranks(const std::string& image, const std::string& out, int64_t H, int64_t W, int C,
+                  const pconv_filter_t& f, int loops, int np, int threads, int depth) {
+    int gr = 0, gc = 0, exact = 0;
+    if (pconv_choose_grid(H, W, np, &gr, &gc, &exact) != 0) {
+        std::fprintf(stderr, "pconv_native: cannot place %d ranks on a %lldx%lld image\n", np, (long long)W, (long long)H);
+        return EXIT_FAILURE;
+    }
+    std::vector<int64_t> r0(gr), nr(gr), c0(gc), nc(gc);
+    int64_t min_ext = H + W;
+    for (int i = 0; i < gr; ++i) { pconv_split(H, gr, i, &r0[i], &nr[i]); min_ext = std::min(min_ext, nr[i]); }
+    for (int j = 0; j < gc; ++j) { pconv_split(W, gc, j, &c0[j], &nc[j]); min_ext = std::min(min_ext, nc[j]); }
+    const int k = (int)std::max<int64_t>(1, std::min<int64_t>(depth > 0 ? depth : 6, min_ext));
+    const int64_t rb = W * C;
+    const std::string seg_path = "/dev/shm/pconv_native_" + std::to_string((long long)getpid());
+    pconv_shm_t* seg = pconv_shm_create(seg_path.c_str(), H, W, C, np);
+    if (!seg) { std::fprintf(stderr, "pconv_native: cannot create %s\n", seg_path.c_str()); return EXIT_FAILURE; }
+    unlink(seg_path.c_str());                 // the mapping is inherited by fork(): the name is not needed
+    if (pconv_create_file(out.c_str(), H * rb) != 0) {
+        std::fprintf(stderr, "pconv_native: cannot create %s\n", out.c_str());
+        return EXIT_FAILURE;
+    }
+    const int64_t pitch = pconv_shm_pitch(seg);
+    std::vector<pid_t> pid((size_t)np, 0);
+    std::fflush(nullptr);
+    for (int r = 0; r < np; ++r) {
+        pid[r] = fork();
+        if (pid[r] < 0) {
+            std::perror("pconv_native: fork");
+            for (int q = 0; q < r; ++q) kill(pid[q], SIGTERM);
+            return EXIT_FAILURE;
+        }
+        if (pid[r] != 0) continue;
+        // ---- rank r ----
+        const int ty = r / gc, tx = r % gc;
+        int32_t nbr[9];
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int y = ty + dy, x = tx + dx;
+                nbr[(dy + 1) * 3 + dx + 1] = (y < 0 || y >= gr || x < 0 || x >= gc) ? -1 : y * gc + x;
+            }
+        uint8_t* img0 = pconv_shm_pixels(seg, 0);
+        int rc = pconv_read_rect(image.c_str(), rb, r0[ty], nr[ty], c0[tx] * C, nc[tx] * C,
+                                 img0 + r0[ty] * pitch + c0[tx] * C, pitch);
+        if (rc != 0) {
+            std::fprintf(stderr, "pconv_native: rank %d cannot read %s (%d)\n", r, image.c_str(), rc);
+            pconv_shm_abort(seg, r);
+            std::_Exit(3);
+        }
+        if (pconv_shm_barrier(seg, 600.0) != 0) std::_Exit(4);      // every tile is in place (mpi_conv.c:159)
+        const double t0 = now_s();
+        rc = pconv_shm_run(seg, r, r0[ty], r0[ty] + nr[ty], c0[tx], c0[tx] + nc[tx], nbr, &f, loops, k,
+                           threads > 0 ? threads : 1, 60.0, nullptr);
+        pconv_shm_set_value(seg, r, now_s() - t0);
+        if (rc != 0) {
+            std::fprintf(stderr, "pconv_native: rank %d: %s\n", r, rc == -110 ? "a neighbour stopped advancing" : "a neighbour gave up");
+            std::_Exit(5);
+        }
+        const uint8_t* res = pconv_shm_pixels(seg, (int)(pconv_shm_epoch(seg, r) & 1));
+        rc = pconv_write_rect(out.c_str(), rb, r0[ty], nr[ty], c0[tx] * C, nc[tx] * C,
+                              res + r0[ty] * pitch + c0[tx] * C, pitch);
+        std::_Exit(rc == 0 ? 0 : 6);
+    }
+    int failed = 0;
+    for (int left = np; left > 0;) {
+        int st = 0;
+        const pid_t w = wait(&st);
+        if (w < 0) break;
+        --left;
+        for (auto& p : pid) if (p == w) p = 0;
+        if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0) && !failed) {
+            failed = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + WTERMSIG(st);
+            for (pid_t p : pid) if (p > 0) kill(p, SIGTERM);       // exactly the processes started here
+        }
+    }
+    if (failed) return failed;
+    double slowest = 0.0;
+    for (int r = 0; r < np; ++r) slowest = std::max(slowest, pconv_shm_get_value(seg, r));
+    std::printf("%f\n", slowest);           // what `mpirun -np N ./mpi_conv` prints (mpi/mpi_conv.c:273-283)
+    return EXIT_SUCCESS;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
+    int np = 1;
+    if (argc >= 3 && (!std::strcmp(argv[1], "-np") || !std::strcmp(argv[1], "-n"))) {
+        np = std::atoi(argv[2]);
+        if (np < 1 || np > 1024) return usage(argv[0]);
+        argv[2] = argv[0];
+        argv += 2;
+        argc -= 2;
+    }
     if (argc < 6) return usage(argv[0]);
     const std::string image = argv[1];
     const int64_t W = std::atoll(argv[2]), H = std::atoll(argv[3]);
@@ -59,12 +158,13 @@ int main(int argc, char** argv) {
     else return usage(argv[0]);
     std::string filter = "gaussian", out;
     bool cpu = false;
-    int threads = 0;
+    int threads = 0, depth = 0;
     long long ooc_mib = 0;   // > 0: stream the file through the CPU engine without loading it
     for (int i = 6; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--filter") && i + 1 < argc) filter = argv[++i];
         else if (!std::strcmp(argv[i], "--cpu")) cpu = true;
         else if (!std::strcmp(argv[i], "--threads") && i + 1 < argc) threads = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--halo-depth") && i + 1 < argc) depth = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--out-of-core") && i + 1 < argc) ooc_mib = std::atoll(argv[++i]);
         else if (!std::strcmp(argv[i], "-o") && i + 1 < argc) out = argv[++i];
         else return usage(argv[0]);
@@ -89,6 +189,14 @@ int main(int argc, char** argv) {
     if (pconv_file_size(image.c_str()) < nbytes) {
         std::fprintf(stderr, "pconv_native: %s is shorter than %lld bytes\n", image.c_str(), (long long)nbytes);
         return EXIT_FAILURE;
+    }
+    if (np > 1) {
+        if (!cpu && pconv_cuda_device_count() > 0) {
+            std::fprintf(stderr, "pconv_native: -np N starts CPU ranks (add --cpu); for N GPUs use "
+                                 "python -m parallel_convolution_b200 -np N ...\n");
+            return EXIT_FAILURE;
+        }
+        return run_cpu_ranks(image, out, H, W, C, f, loops, np, threads, depth);
     }
     if (ooc_mib > 0) {   // images larger than memory: file -> file through row strips (cpu_engine.cpp)
         const double t0 = now_s();
