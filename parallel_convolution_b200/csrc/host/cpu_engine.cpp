@@ -11,6 +11,7 @@
 //   * OpenMP parallelises rows with one parallel region per pass (the reference opens one per
 //     convolute() call, including 1x1 corner calls, and its pragma does not compile: defect D7).
 #include <omp.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdint>
@@ -170,15 +171,20 @@ extern "C" void pconv_cpu_band_advance(const uint8_t* src0, uint8_t* dst0, int64
         std::memcpy(dst0 + y * pitch + c0 * C, xa + (y - lo) * lpitch + (c0 - bl) * C, (size_t)((c1 - c0) * C));
 }
 
-static int run_image_blocked(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
-                             const pconv_filter_t* f, int loops, int threads, int k) {
-    const int64_t rb = W * (int64_t)C;
-    const int64_t pitch = ((rb + 2 * C + 63) / 64) * 64;
+// Advance a padded image pair: pa/pb point at pixel (0,0) of two (H + 2) x pitch images whose 1-pixel frame
+// is zero (and stays zero); the input is in pa. k <= 1: one pass over the whole image per iteration; k > 1:
+// bands advance k iterations in cache-sized private buffers. Returns 0 / 1 = the result is in pa / pb.
+extern "C" int pconv_cpu_run_padded(uint8_t* pa, uint8_t* pb, int64_t pitch, int64_t H, int64_t W, int C,
+                                    const pconv_filter_t* f, int loops, int threads, int k) {
+    if (!pa || !pb || !f || H <= 0 || W <= 0 || C <= 0 || loops < 0) return -1;
     const int nt = threads > 0 ? threads : omp_get_max_threads();
-    std::vector<uint8_t> ga((size_t)((H + 2) * pitch), 0), gb((size_t)((H + 2) * pitch), 0);
-    uint8_t* pa = ga.data() + pitch + C;   // pixel (0,0) of the global ping-pong images
-    uint8_t* pb = gb.data() + pitch + C;
-    for (int64_t y = 0; y < H; ++y) std::memcpy(pa + y * pitch, src + y * rb, (size_t)rb);
+    if (k <= 1) {
+        for (int t = 0; t < loops; ++t) {
+            pconv_cpu_convolve(pa, pb, pitch, C, f, 0, H, 0, W, nt);
+            std::swap(pa, pb);
+        }
+        return loops & 1;
+    }
     // band height: both private buffers (band + 2k halo rows) should sit in ~1 MB of L2
     int64_t band = (int64_t)(1 << 20) / (2 * pitch) - 2 * k;
     band = std::max<int64_t>(band, 8);
@@ -202,9 +208,32 @@ static int run_image_blocked(const uint8_t* src, uint8_t* dst, int64_t H, int64_
             done += kk;      // the implicit barrier of the loop separates the passes
         }
     }
-    const uint8_t* last = ((loops + k - 1) / k) & 1 ? pb : pa;
+    return ((loops + k - 1) / k) & 1;
+}
+
+extern "C" int64_t pconv_cpu_padded_pitch(int64_t W, int C) { return ((W * (int64_t)C + 2 * C + 63) / 64) * 64; }
+
+// Dense image in, dense image out: padded ping-pong images around pconv_cpu_run_padded.
+static int run_image_k(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
+                       const pconv_filter_t* f, int loops, int threads, int k) {
+    const int64_t rb = W * (int64_t)C;
+    const int64_t pitch = pconv_cpu_padded_pitch(W, C);
+    // Two zero-initialised padded buffers: the 1-pixel frame stays 0 forever = zero padding
+    // (same device the reference uses: calloc'd (rows+2)x(cols+2) tiles, mpi/mpi_conv.c:113-124).
+    std::vector<uint8_t> ga((size_t)((H + 2) * pitch), 0), gb((size_t)((H + 2) * pitch), 0);
+    uint8_t* pa = ga.data() + pitch + C;   // pixel (0,0) of the global ping-pong images
+    uint8_t* pb = gb.data() + pitch + C;
+    for (int64_t y = 0; y < H; ++y) std::memcpy(pa + y * pitch, src + y * rb, (size_t)rb);
+    const int which = pconv_cpu_run_padded(pa, pb, pitch, H, W, C, f, loops, threads, k);
+    if (which < 0) return which;
+    const uint8_t* last = which ? pb : pa;
     for (int64_t y = 0; y < H; ++y) std::memcpy(dst + y * rb, last + y * pitch, (size_t)rb);
     return 0;
+}
+
+static int run_image_blocked(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
+                             const pconv_filter_t* f, int loops, int threads, int k) {
+    return run_image_k(src, dst, H, W, C, f, loops, threads, k);
 }
 
 extern "C" int pconv_cpu_run_image_blocked(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W,
@@ -272,27 +301,26 @@ extern "C" int pconv_cpu_run_file(const char* in_path, const char* out_path, int
     return rc;
 }
 
+extern "C" int pconv_cpu_blocking_depth(int64_t H, int64_t W, int C, int loops) {
+    // Temporal blocking pays when the two padded images do not fit in the last-level cache: then every plain pass
+    // streams the image through memory, and k iterations per pass divide that traffic by k. Cache-resident images
+    // are faster with plain passes (no band copies, no redundant halo rows).
+    static const int64_t llc = [] {
+        long v = sysconf(_SC_LEVEL3_CACHE_SIZE);
+        if (v <= 0) v = sysconf(_SC_LEVEL2_CACHE_SIZE);
+        return (int64_t)(v > 0 ? v : (32 << 20));
+    }();
+    if (const char* e = std::getenv("PCONV_CPU_BLOCK_DEPTH")) return std::max(1, std::atoi(e));
+    const int64_t bytes = 2 * (H + 2) * pconv_cpu_padded_pitch(W, C);
+    return (loops >= 4 && bytes > llc) ? std::min(loops, 6) : 1;
+}
+
 extern "C" int pconv_cpu_run_image(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
                                    const pconv_filter_t* f, int loops, int threads) {
     if (!src || !dst || !f || H <= 0 || W <= 0 || C <= 0 || loops < 0) return -1;
-    const int64_t rb = W * (int64_t)C;
     if (loops == 0) {
-        std::memcpy(dst, src, (size_t)(H * rb));
+        std::memcpy(dst, src, (size_t)(H * W * C));
         return 0;
     }
-    if (loops >= 4 && H * rb >= (4 << 20))   // big enough to be memory-bound: block in time
-        return run_image_blocked(src, dst, H, W, C, f, loops, threads, std::min(loops, 6));
-    // Two zero-initialised padded buffers: the 1-pixel frame stays 0 forever = zero padding
-    // (same device the reference uses: calloc'd (rows+2)x(cols+2) tiles, mpi/mpi_conv.c:113-124).
-    const int64_t pitch = ((rb + 2 * C + 63) / 64) * 64;
-    std::vector<uint8_t> a((size_t)((H + 2) * pitch), 0), b((size_t)((H + 2) * pitch), 0);
-    uint8_t* pa = a.data() + pitch + C;
-    uint8_t* pb = b.data() + pitch + C;
-    for (int64_t y = 0; y < H; ++y) std::memcpy(pa + y * pitch, src + y * rb, (size_t)rb);
-    for (int t = 0; t < loops; ++t) {
-        pconv_cpu_convolve(pa, pb, pitch, C, f, 0, H, 0, W, threads);
-        std::swap(pa, pb);
-    }
-    for (int64_t y = 0; y < H; ++y) std::memcpy(dst + y * rb, pa + y * pitch, (size_t)rb);
-    return 0;
+    return run_image_k(src, dst, H, W, C, f, loops, threads, pconv_cpu_blocking_depth(H, W, C, loops));
 }

@@ -70,6 +70,16 @@ int pconv_cpu_convolve(const uint8_t* src0, uint8_t* dst0, int64_t pitch, int C,
 // Whole dense image, `loops` iterations, zero padded, multi-threaded; dst receives the result.
 int pconv_cpu_run_image(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
                         const pconv_filter_t* f, int loops, int threads);
+// The loop alone, on caller-owned padded images (what a timer should bracket; the reference times its loop the
+// same way, after the calloc and the file read: mpi/mpi_conv.c:113-162): pa/pb = pixel (0,0) of two (H+2) x
+// pitch images with a zero 1-pixel frame, pitch = pconv_cpu_padded_pitch(W, C), input in pa. k <= 1 plain
+// passes, k > 1 temporally blocked. Returns 0 / 1: the result is in pa / pb; < 0 on bad arguments.
+int pconv_cpu_run_padded(uint8_t* pa, uint8_t* pb, int64_t pitch, int64_t H, int64_t W, int C,
+                         const pconv_filter_t* f, int loops, int threads, int k);
+int64_t pconv_cpu_padded_pitch(int64_t W, int C);
+// The depth pconv_cpu_run_image picks: 1 while both padded images fit in the last-level cache, else up to 6
+// (PCONV_CPU_BLOCK_DEPTH overrides).
+int pconv_cpu_blocking_depth(int64_t H, int64_t W, int C, int loops);
 // Same result, temporally blocked: row bands advance k iterations in L2-sized private buffers
 // (pconv_cpu_run_image picks this automatically for memory-bound sizes).
 int pconv_cpu_run_image_blocked(const uint8_t* src, uint8_t* dst, int64_t H, int64_t W, int C,
