@@ -3,7 +3,8 @@
 exchange per iteration (k=1) or the planner's depth (--halo-depth 0): the fused backend (persistent kernel
 with pushed halos where the tile fits on chip, streaming kernel with pulled halos otherwise) vs the NCCL
 send/recv baseline (one pack kernel + one ncclGroup + one unpack kernel per exchange, whole run replayed
-as a CUDA graph) vs the MPI-like host backend over gloo (--with-cpu, small edges only).
+as a CUDA graph) vs the MPI-like host backend (--with-cpu, small edges only: `cpu` = gloo messages, `cpu:shm` = CPU
+ranks over the shared image; the CPU-only sweep incl. the reference's own mpi_conv is bench/halo_sweep_cpu.py).
 
 For every tile edge E the image is (grid_rows*E) x (grid_cols*E) grey pixels, so every rank owns
 an E x E tile. Reported per backend: device time per iteration (max over ranks), the same tile's
@@ -48,14 +49,16 @@ def main():
     for E in [int(v) for v in a.edges.split(",")]:
         W, Hh = gc * E, gr * E
         row = {"tile_edge": E, "gpus": world, "grid": f"{gr}x{gc}", "k": a.halo_depth, "loops": a.loops}
-        arms = a.backends.split(",") + (["cpu"] if a.with_cpu and E <= 1024 else [])
+        arms = a.backends.split(",") + (["cpu", "cpu:shm"] if a.with_cpu and E <= 1024 else [])
         done = []
         for arm in arms:
             be, _, mode = arm.partition(":")
             key = arm.replace(":", "_")
             try:
+                transport = ("shm" if mode == "shm" else "gloo") if be == "cpu" else "auto"   # cpu = messages, cpu:shm = shared image
                 eng = ConvEngine(width=W, height=Hh, channels=a.channels, filter="gaussian", backend=be,
-                                 grid=(gr, gc), halo_depth=a.halo_depth or None, mode=mode or "auto", device=local)
+                                 grid=(gr, gc), halo_depth=a.halo_depth or None,
+                                 mode="auto" if be == "cpu" else (mode or "auto"), cpu_transport=transport, device=local)
                 best = None
                 for _ in range(3):
                     eng.load_synthetic(1)
