@@ -163,3 +163,49 @@ def test_emulated_exchange_random_rank_grids(gy, gx, tile_h, tile_chunks, c, k, 
         assert got in (-2, -4), got         # band too short for the halo / last CTA row or column too thin
         return
     assert np.array_equal(got, host.oracle(img, f.spec, loops))
+
+
+@settings(max_examples=30, deadline=None)
+@given(h=st.integers(6, 70), w=st.integers(6, 70), c=st.sampled_from([1, 3, 4]), gr=st.integers(1, 3), gc=st.integers(1, 3),
+       k=st.integers(1, 7), loops=st.integers(0, 11), threads=st.integers(1, 2),
+       filt=st.sampled_from(["gaussian", "box", "sharpen", "edge"]), seed=st.integers(0, 2**31))
+def test_shared_image_ranks_random_geometry(h, w, c, gr, gc, k, loops, threads, filt, seed):
+    """CPU ranks over the shared image (csrc/host/shm_ranks.cpp), ranks = threads of this process: any grid with
+    remainder tiles, any depth up to the smallest tile, any iteration count -> the oracle's bytes."""
+    import os
+    import threading
+    from parallel_convolution_b200.parallel.shm_backend import ShmTile
+    if h < gr * 2 or w < gc * 2:
+        return
+    g = TileGrid.create(h, w, c, gr * gc, (gr, gc))
+    k = min(k, g.min_tile_rows(), g.min_tile_cols()) if gr * gc > 1 else k
+    f = Filter.builtin(filt)
+    img = np.random.default_rng(seed).integers(0, 256, (h, w * c), dtype=np.uint8)
+    path = f"/dev/shm/pconv_prop_{os.getpid()}_{seed}_{h}_{w}"
+    seg = host.ShmSegment(path, h, w, c, gr * gc, create=True)
+    os.unlink(path)
+    tiles = [ShmTile(g, r, f, k, threads, None, 20_000.0, segment=seg) for r in range(gr * gc)]
+    for t in tiles:
+        tt = t.tile
+        seg.reset(t.rank)
+        t._view(0)[:] = img[tt.row0:tt.row0 + tt.rows, tt.col0 * c:(tt.col0 + tt.cols) * c]
+    errs = []
+
+    def work(t):
+        try:
+            t.iterate(loops)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in tiles]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs
+    out = np.empty_like(img)
+    for t in tiles:
+        tt = t.tile
+        out[tt.row0:tt.row0 + tt.rows, tt.col0 * c:(tt.col0 + tt.cols) * c] = t.result()
+    shape = (h, w) if c == 1 else (h, w, c)
+    want = host.oracle(img.reshape(shape), f.spec, loops).reshape(h, w * c)
+    seg.close()
+    assert np.array_equal(out, want)
