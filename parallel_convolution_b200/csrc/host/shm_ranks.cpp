@@ -144,8 +144,10 @@ extern "C" pconv_shm_t* pconv_shm_create(const char* path, int64_t H, int64_t W,
     h.total_bytes = h.off_image[1] + h.image_bytes;
     const int fd = open(path, O_CREAT | O_EXCL | O_RDWR | O_CLOEXEC, 0600);
     if (fd < 0) return nullptr;
-    if (ftruncate(fd, (off_t)h.total_bytes) != 0) {      // zero pages: the 1-pixel frame of both images is the
-        close(fd);                                        // zero padding and is never written afterwards
+    // posix_fallocate, not ftruncate: tmpfs must really have the room (ENOSPC now instead of SIGBUS at the first
+    // touch). The pages come back zeroed: the 1-pixel frame of both images is the zero padding and is never written.
+    if (posix_fallocate(fd, 0, (off_t)h.total_bytes) != 0) {
+        close(fd);
         unlink(path);
         return nullptr;
     }

@@ -134,10 +134,10 @@ class ConvEngine:
             return "local"
         if want == "gloo":
             return "gloo"
-        from .parallel.shm_backend import same_node
-        ok = same_node(self.dist)                 # collective: every rank takes the same branch
+        from .parallel.shm_backend import same_node, segment_bytes
+        ok = same_node(self.dist, segment_bytes(self.grid))   # collective: every rank takes the same branch
         if want == "shm" and not ok:
-            raise RuntimeError("cpu transport 'shm' needs every rank on one node with /dev/shm")
+            raise RuntimeError("cpu transport 'shm' needs every rank on one node and room for both images in /dev/shm")
         return "shm" if ok else "gloo"
 
     def _setup(self) -> None:

@@ -25,16 +25,31 @@ from .decomposition import TileGrid
 DEFAULT_DEPTH = 6          # iterations per epoch when the caller does not choose (as pconv_cpu_run_image)
 
 
-def same_node(dist) -> bool:
-    """True when every rank of the process group runs on this machine (shared memory is reachable)."""
+def segment_bytes(grid: TileGrid) -> int:
+    """Size of the shared segment for this image: two padded images plus a few pages of counters."""
+    C = grid.channels
+    pitch = (grid.width * C + 2 * C + 63) // 64 * 64
+    return 2 * (((grid.height + 2) * pitch + 4095) // 4096 * 4096) + 4096 * (2 + grid.workers // 64)
+
+
+def same_node(dist, need_bytes: int = 0) -> bool:
+    """True when every rank of the process group runs on this machine and /dev/shm can hold ``need_bytes``
+    (shared memory is reachable and large enough; container defaults can be as small as 64 MiB)."""
     try:
         boot = open("/proc/sys/kernel/random/boot_id").read().strip()
     except OSError:
         boot = ""
-    me = f"{socket.gethostname()}|{boot}|{os.path.exists('/dev/shm')}"
+    room = False
+    if os.path.isdir("/dev/shm"):
+        try:
+            v = os.statvfs("/dev/shm")
+            room = v.f_bavail * v.f_frsize >= need_bytes + (16 << 20)
+        except OSError:
+            room = False
+    me = f"{socket.gethostname()}|{boot}"
     names = [None] * dist.get_world_size()
-    dist.all_gather_object(names, me)
-    return all(n == me for n in names) and os.path.isdir("/dev/shm")
+    dist.all_gather_object(names, (me, room))
+    return all(n == me and ok for n, ok in names)
 
 
 class ShmTile:
@@ -70,13 +85,26 @@ class ShmTile:
         seg = None
         if self.rank == 0:
             box[0] = f"/dev/shm/pconv_{os.getpid()}_{uuid.uuid4().hex[:12]}"
-            seg = H.ShmSegment(box[0], g.height, g.width, g.channels, g.workers, create=True)
+            try:
+                seg = H.ShmSegment(box[0], g.height, g.width, g.channels, g.workers, create=True)
+            except OSError:
+                box[0] = None          # tell the others instead of leaving them in the broadcast
         dist.broadcast_object_list(box, src=0)
+        if box[0] is None:
+            raise OSError("rank 0 could not create the shared image in /dev/shm (no room?); "
+                          "use --cpu-transport gloo")
+        ok = True
         if self.rank != 0:
-            seg = H.ShmSegment(box[0])
-        dist.barrier()
+            try:
+                seg = H.ShmSegment(box[0])
+            except OSError:
+                ok = False
+        oks = [None] * dist.get_world_size()
+        dist.all_gather_object(oks, ok)  # also the barrier: every rank has mapped the segment (or failed to)
         if self.rank == 0:
             os.unlink(box[0])          # mapped everywhere: nothing is left behind if a rank dies
+        if not all(oks):
+            raise OSError("a rank could not attach to the shared image; use --cpu-transport gloo")
         return seg
 
     # -- tile I/O -----------------------------------------------------------------------------
