@@ -37,7 +37,7 @@ def _pick_cxx() -> str:
 CXX = _pick_cxx()
 
 HOST_SOURCES = ["host/filters.cpp", "host/decomp.cpp", "host/cpu_engine.cpp", "host/rawio.cpp",
-                "host/planner.cpp", "host/xplan_emu.cpp", "host/shm_ranks.cpp"]
+                "host/planner.cpp", "host/xplan_emu.cpp", "host/shm_ranks.cpp", "host/net_ranks.cpp"]
 HOST_ORACLE = "host/oracle.cpp"  # compiled separately at -O1 with contraction off
 CUDA_SOURCES = ["cuda/runtime.cu", "cuda/pack_kernels.cu", "cuda/stream_kernel.cu", "cuda/persist_kernel.cu",
                 "cuda/stream_kind_sep.cu", "cuda/stream_kind_int.cu", "cuda/stream_kind_f32.cu",

@@ -127,6 +127,25 @@ int pconv_shm_run(pconv_shm_t* s, int rank, int64_t r0, int64_t r1, int64_t c0, 
                   const int32_t nbr[9], const pconv_filter_t* f, int loops, int k, int threads,
                   double timeout_s, int64_t* epochs_run);
 
+// ---- CPU ranks with private tiles and TCP messages (csrc/host/net_ranks.cpp) --------------------------
+// For ranks that do not share a node: full mesh of TCP connections, rendezvous through rank 0
+// (master_host:master_port; master_fd >= 0 hands rank 0 an already listening socket), k-deep halo exchange
+// with the reference's schedule (send -> halo-free part of the first iteration -> wait -> frame).
+typedef struct pconv_net pconv_net_t;
+pconv_net_t* pconv_net_init(int rank, int world, const char* master_host, int master_port, int master_fd,
+                            double timeout_s);
+void pconv_net_close(pconv_net_t* n);
+const char* pconv_net_error(const pconv_net_t* n);
+int pconv_net_barrier(pconv_net_t* n);
+int pconv_net_max(pconv_net_t* n, double* v);            // in place: the maximum over all ranks, on every rank
+int64_t pconv_net_tile_pitch(int64_t cols, int C, int k);
+// buf_a / buf_b: two ZEROED buffers of (rows + 2k) * pitch bytes, the tile's pixel (0,0) at row k, byte k*C, the
+// input tile in buf_a; nbr[9] as in pconv_shm_run; k <= the smallest tile extent. Returns 0 / 1 = the result is in
+// buf_a / buf_b, or a negative errno (pconv_net_error says why).
+int pconv_net_run(pconv_net_t* n, int64_t H, int64_t W, int C, int64_t row0, int64_t rows, int64_t col0,
+                  int64_t cols, const int32_t nbr[9], uint8_t* buf_a, uint8_t* buf_b, const pconv_filter_t* f,
+                  int loops, int k, int threads, int64_t* exchanges);
+
 // ---- raw image I/O (64-bit offsets; reference: MPI_File_* mpi/mpi_conv.c:133-147,253-271) ----
 int64_t pconv_file_size(const char* path);
 // Read a rectangle: rows [row0,row0+nrows), bytes [byte0,byte0+nbytes) of every row of a file

@@ -3,17 +3,24 @@
 //
 //   pconv_native [-np N] image width height loops {rgb|grey} [--filter NAME] [--cpu] [--threads T]
 //                [--halo-depth K] [--out-of-core MiB] [-o OUT]
+//                [--transport shm|tcp] [--rank R --world N --master HOST:PORT]
 //
 // `-np N` (with --cpu, or on a box without a GPU) is `mpirun -np N ./mpi_conv ...` (mpi/READ_ME.txt:4-5) without
 // MPI and without Python: N processes forked over one shared image (host/shm_ranks.cpp), every rank reads its
 // tile rows from the file, iterates, and writes them back (the reference's MPI_File_* pattern,
 // mpi/mpi_conv.c:133-147,253-271); the time printed is the iteration loop, max over ranks.
+// `--transport tcp` gives the ranks private tiles and TCP messages instead (host/net_ranks.cpp) — the form that
+// also spans nodes: start one process per rank anywhere with `--rank R --world N --master HOST:PORT` (or RANK /
+// WORLD_SIZE / MASTER_ADDR / MASTER_PORT in the environment, as torchrun and most schedulers export them); the
+// image and the output must be on a file system all ranks see, as with the reference's MPI-IO.
 //
 // Same positional grammar and the same "Execution time: %.3f sec" line (whole program: file read,
 // H2D, kernels, D2H, file write — cuda/main.c:20,48-50), plus the loop-only seconds on a second
 // line. Everything is the same native code the Python package drives: raw I/O, filter
 // classification and launch planning from libpconv_host.so, kernels from libpconv_cuda.so.
+#include <netinet/in.h>
 #include <signal.h>
+#include <sys/socket.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -39,7 +46,8 @@ const Builtin kBuiltins[] = {
 
 int usage(const char* prog) {
     std::fprintf(stderr, "Error Input!\n%s [-np N] image_name width height loops [rgb/grey] "
-                         "[--filter NAME] [--cpu] [--threads T] [--halo-depth K] [--out-of-core MiB] [-o OUT]\n", prog);
+                         "[--filter NAME] [--cpu] [--threads T] [--halo-depth K] [--out-of-core MiB] [-o OUT] "
+                         "[--transport shm|tcp] [--rank R --world N --master HOST:PORT] [--net-timeout S]\n", prog);
     return EXIT_FAILURE;
 }
 
@@ -54,6 +62,23 @@ double now_s() {
             return EXIT_FAILURE;                                                      \
         }                                                                             \
     } while (0)
+
+// Reap the forked ranks; when one fails, stop the others (exactly the PIDs started here) and report its status.
+int wait_for_ranks(std::vector<pid_t>& pid) {
+    int failed = 0;
+    for (size_t left = pid.size(); left > 0;) {
+        int st = 0;
+        const pid_t w = wait(&st);
+        if (w < 0) break;
+        --left;
+        for (auto& p : pid) if (p == w) p = 0;
+        if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0) && !failed) {
+            failed = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + WTERMSIG(st);
+            for (pid_t p : pid) if (p > 0) kill(p, SIGTERM);
+        }
+    }
+    return failed;
+}
 
 // N CPU ranks over one shared image. Returns the process exit code.
 int run_cpu_ranks(const std::string& image, const std::string& out, int64_t H, int64_t W, int C,
@@ -118,23 +143,97 @@ int run_cpu_ranks(const std::string& image, const std::string& out, int64_t H, i
                               res + r0[ty] * pitch + c0[tx] * C, pitch);
         std::_Exit(rc == 0 ? 0 : 6);
     }
-    int failed = 0;
-    for (int left = np; left > 0;) {
-        int st = 0;
-        const pid_t w = wait(&st);
-        if (w < 0) break;
-        --left;
-        for (auto& p : pid) if (p == w) p = 0;
-        if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0) && !failed) {
-            failed = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + WTERMSIG(st);
-            for (pid_t p : pid) if (p > 0) kill(p, SIGTERM);       // exactly the processes started here
-        }
-    }
-    if (failed) return failed;
+    if (const int failed = wait_for_ranks(pid)) return failed;
     double slowest = 0.0;
     for (int r = 0; r < np; ++r) slowest = std::max(slowest, pconv_shm_get_value(seg, r));
     std::printf("%f\n", slowest);           // what `mpirun -np N ./mpi_conv` prints (mpi/mpi_conv.c:273-283)
     return EXIT_SUCCESS;
+}
+
+// One CPU rank with a private tile and TCP messages to its neighbours (host/net_ranks.cpp). Every rank of the job
+// runs this, in a forked child (-np N --transport tcp) or as its own process on any node (--rank/--world/--master).
+int run_tcp_rank(const std::string& image, const std::string& out, int64_t H, int64_t W, int C,
+                 const pconv_filter_t& f, int loops, int rank, int world, const std::string& master_host,
+                 int master_port, int master_fd, int threads, int depth, double net_timeout_s) {
+    int gr = 0, gc = 0, exact = 0;
+    if (pconv_choose_grid(H, W, world, &gr, &gc, &exact) != 0) {
+        std::fprintf(stderr, "pconv_native: cannot place %d ranks on a %lldx%lld image\n", world, (long long)W, (long long)H);
+        return EXIT_FAILURE;
+    }
+    int64_t min_ext = H + W;
+    for (int i = 0; i < gr; ++i) { int64_t a, b; pconv_split(H, gr, i, &a, &b); min_ext = std::min(min_ext, b); }
+    for (int j = 0; j < gc; ++j) { int64_t a, b; pconv_split(W, gc, j, &a, &b); min_ext = std::min(min_ext, b); }
+    const int k = (int)std::max<int64_t>(1, std::min<int64_t>(depth > 0 ? depth : 6, world > 1 ? min_ext : 1));
+    const int ty = rank / gc, tx = rank % gc;
+    int64_t row0, rows, col0, cols;
+    pconv_split(H, gr, ty, &row0, &rows);
+    pconv_split(W, gc, tx, &col0, &cols);
+    int32_t nbr[9];
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int y = ty + dy, x = tx + dx;
+            nbr[(dy + 1) * 3 + dx + 1] = (y < 0 || y >= gr || x < 0 || x >= gc) ? -1 : y * gc + x;
+        }
+    pconv_net_t* net = pconv_net_init(rank, world, master_host.c_str(), master_port, master_fd, net_timeout_s);
+    if (!net) return 7;
+    const int64_t rb = W * C, pitch = pconv_net_tile_pitch(cols, C, k);
+    std::vector<uint8_t> a((size_t)((rows + 2 * k) * pitch), 0), b(a.size(), 0);
+    int rc = pconv_read_rect(image.c_str(), rb, row0, rows, col0 * C, cols * C, a.data() + k * pitch + (int64_t)k * C, pitch);
+    if (rc != 0) {
+        std::fprintf(stderr, "pconv_native: rank %d cannot read %s (%d)\n", rank, image.c_str(), rc);
+        return 3;
+    }
+    if (rank == 0 && pconv_create_file(out.c_str(), H * rb) != 0) {
+        std::fprintf(stderr, "pconv_native: cannot create %s\n", out.c_str());
+        return 6;
+    }
+    if (pconv_net_barrier(net) != 0) { std::fprintf(stderr, "pconv_native: rank %d: %s\n", rank, pconv_net_error(net)); return 4; }
+    const double t0 = now_s();
+    const int which = pconv_net_run(net, H, W, C, row0, rows, col0, cols, nbr, a.data(), b.data(), &f, loops, k,
+                                    threads > 0 ? threads : 1, nullptr);
+    double dt = now_s() - t0;
+    if (which < 0) { std::fprintf(stderr, "pconv_native: rank %d: %s\n", rank, pconv_net_error(net)); return 5; }
+    if (pconv_net_max(net, &dt) != 0) { std::fprintf(stderr, "pconv_native: rank %d: %s\n", rank, pconv_net_error(net)); return 5; }
+    const uint8_t* res = (which ? b : a).data() + k * pitch + (int64_t)k * C;
+    rc = pconv_write_rect(out.c_str(), rb, row0, rows, col0 * C, cols * C, res, pitch);
+    if (rc == 0) rc = pconv_net_barrier(net);         // the output is complete when rank 0 reports the time
+    if (rank == 0 && rc == 0) std::printf("%f\n", dt);   // mpi/mpi_conv.c:273-283: max over ranks, printed once
+    std::fflush(stdout);
+    pconv_net_close(net);
+    return rc == 0 ? EXIT_SUCCESS : 6;
+}
+
+// -np N --transport tcp on one node: the parent opens the rendezvous socket, forks the ranks, reaps them.
+int run_tcp_ranks_local(const std::string& image, const std::string& out, int64_t H, int64_t W, int C,
+                        const pconv_filter_t& f, int loops, int np, int threads, int depth, double net_timeout_s) {
+    const int lfd = socket(AF_INET, SOCK_STREAM, 0);
+    sockaddr_in addr{};
+    addr.sin_family = AF_INET;
+    addr.sin_addr.s_addr = htonl(INADDR_LOOPBACK);
+    socklen_t len = sizeof addr;
+    if (lfd < 0 || bind(lfd, (sockaddr*)&addr, sizeof addr) != 0 || listen(lfd, np + 8) != 0 ||
+        getsockname(lfd, (sockaddr*)&addr, &len) != 0) {
+        std::perror("pconv_native: rendezvous socket");
+        return EXIT_FAILURE;
+    }
+    const int port = ntohs(addr.sin_port);
+    std::vector<pid_t> pid((size_t)np, 0);
+    std::fflush(nullptr);
+    for (int r = 0; r < np; ++r) {
+        pid[r] = fork();
+        if (pid[r] < 0) {
+            std::perror("pconv_native: fork");
+            for (int q = 0; q < r; ++q) kill(pid[q], SIGTERM);
+            return EXIT_FAILURE;
+        }
+        if (pid[r] == 0) {
+            if (r != 0) close(lfd);
+            std::_Exit(run_tcp_rank(image, out, H, W, C, f, loops, r, np, "127.0.0.1", port, r == 0 ? lfd : -1, threads, depth,
+                                    net_timeout_s));
+        }
+    }
+    close(lfd);
+    return wait_for_ranks(pid);
 }
 
 }  // namespace
@@ -158,13 +257,26 @@ int main(int argc, char** argv) {
     else return usage(argv[0]);
     std::string filter = "gaussian", out;
     bool cpu = false;
-    int threads = 0, depth = 0;
+    int threads = 0, depth = 0, rank = -1, world = 0, master_port = 0;
+    std::string transport = "shm", master_host;
+    double net_timeout_s = 120.0;      // rendezvous deadline and longest silence of a peer (tcp transport)
     long long ooc_mib = 0;   // > 0: stream the file through the CPU engine without loading it
     for (int i = 6; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--filter") && i + 1 < argc) filter = argv[++i];
         else if (!std::strcmp(argv[i], "--cpu")) cpu = true;
         else if (!std::strcmp(argv[i], "--threads") && i + 1 < argc) threads = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--halo-depth") && i + 1 < argc) depth = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--transport") && i + 1 < argc) transport = argv[++i];
+        else if (!std::strcmp(argv[i], "--net-timeout") && i + 1 < argc) net_timeout_s = std::atof(argv[++i]);
+        else if (!std::strcmp(argv[i], "--rank") && i + 1 < argc) rank = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--world") && i + 1 < argc) world = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--master") && i + 1 < argc) {
+            const std::string m = argv[++i];
+            const size_t colon = m.rfind(':');
+            if (colon == std::string::npos) return usage(argv[0]);
+            master_host = m.substr(0, colon);
+            master_port = std::atoi(m.c_str() + colon + 1);
+        }
         else if (!std::strcmp(argv[i], "--out-of-core") && i + 1 < argc) ooc_mib = std::atoll(argv[++i]);
         else if (!std::strcmp(argv[i], "-o") && i + 1 < argc) out = argv[++i];
         else return usage(argv[0]);
@@ -190,12 +302,25 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "pconv_native: %s is shorter than %lld bytes\n", image.c_str(), (long long)nbytes);
         return EXIT_FAILURE;
     }
+    if (transport != "shm" && transport != "tcp") return usage(argv[0]);
+    if (np == 1 && (rank >= 0 || transport == "tcp")) {
+        // one rank of a job whose ranks are started separately (any node): explicit flags, else the launcher's env
+        auto env_int = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
+        if (rank < 0) rank = env_int("RANK", -1);
+        if (world <= 0) world = env_int("WORLD_SIZE", 0);
+        if (master_host.empty()) { const char* v = std::getenv("MASTER_ADDR"); master_host = v ? v : "127.0.0.1"; }
+        if (master_port <= 0) master_port = env_int("MASTER_PORT", 0);
+        if (rank < 0 || world < 1 || rank >= world || (world > 1 && master_port <= 0)) return usage(argv[0]);
+        return run_tcp_rank(image, out, H, W, C, f, loops, rank, world, master_host, master_port, -1, threads, depth,
+                            net_timeout_s);
+    }
     if (np > 1) {
         if (!cpu && pconv_cuda_device_count() > 0) {
             std::fprintf(stderr, "pconv_native: -np N starts CPU ranks (add --cpu); for N GPUs use "
                                  "python -m parallel_convolution_b200 -np N ...\n");
             return EXIT_FAILURE;
         }
+        if (transport == "tcp") return run_tcp_ranks_local(image, out, H, W, C, f, loops, np, threads, depth, net_timeout_s);
         return run_cpu_ranks(image, out, H, W, C, f, loops, np, threads, depth);
     }
     if (ooc_mib > 0) {   // images larger than memory: file -> file through row strips (cpu_engine.cpp)
