@@ -61,9 +61,10 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--autotune", action="store_true",
                    help="fused backend: measure candidate launch plans on this machine before the run")
     p.add_argument("--threads", type=int, default=0, help="cpu backend: OpenMP threads per rank")
-    p.add_argument("--cpu-transport", default="auto", choices=["auto", "shm", "gloo"],
-                   help="cpu backend with several ranks: halos through a shared image in /dev/shm (one node; "
-                        "auto picks it when possible) or as gloo messages")
+    p.add_argument("--cpu-transport", default="auto", choices=["auto", "shm", "tcp", "gloo"],
+                   help="cpu backend with several ranks: halos through a shared image in /dev/shm (one node; auto "
+                        "picks it when possible), as messages over the native TCP mesh (any nodes; auto otherwise) "
+                        "or as gloo messages")
     p.add_argument("--out-of-core", type=int, default=None, metavar="MiB",
                    help="cpu backend, single process: stream the file through row strips with k-deep halos, "
                         "holding at most ~MiB of the image in memory (images larger than RAM)")

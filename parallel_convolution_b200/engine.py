@@ -43,7 +43,7 @@ class EngineConfig:
     mode: str = "auto"               # fused backend: auto | stream | resident (persistent kernel)
     warps: int | None = None         # persistent kernel: warps per CTA (8 | 16; None: planner/autotuner)
     threads: int = 0                 # cpu backend: OpenMP threads per rank
-    cpu_transport: str = "auto"      # cpu backend, several ranks: auto | shm (shared image, one node) | gloo (messages)
+    cpu_transport: str = "auto"      # cpu backend, several ranks: auto | shm (shared image, one node) | tcp (native messages) | gloo
     device: int | None = None        # CUDA device index (default: LOCAL_RANK or 0)
     timeout_ms: float = 10_000.0     # in-kernel watchdog for neighbour flags
     slots: int = 1                   # buffer sets for pipelined streaming steps (H2D || iterate || D2H)
@@ -126,19 +126,20 @@ class ConvEngine:
 
     def _pick_cpu_transport(self, want: str) -> str:
         """How CPU ranks trade halos: through a shared image when they all sit on one node (no messages, see
-        parallel/shm_backend.py), as gloo messages otherwise (the reference's MPI schedule)."""
+        parallel/shm_backend.py); otherwise private tiles and messages with the reference's MPI schedule — over the
+        native TCP mesh (parallel/net_backend.py), or over gloo driven from Python (parallel/host_backend.py)."""
         want = os.environ.get("PCONV_CPU_TRANSPORT", want or "auto")
-        if want not in ("auto", "shm", "gloo"):
+        if want not in ("auto", "shm", "tcp", "gloo"):
             raise ValueError(f"unknown cpu transport {want!r}")
         if not self.distributed:
             return "local"
-        if want == "gloo":
-            return "gloo"
+        if want in ("gloo", "tcp"):
+            return want
         from .parallel.shm_backend import same_node, segment_bytes
         ok = same_node(self.dist, segment_bytes(self.grid))   # collective: every rank takes the same branch
         if want == "shm" and not ok:
             raise RuntimeError("cpu transport 'shm' needs every rank on one node and room for both images in /dev/shm")
-        return "shm" if ok else "gloo"
+        return "shm" if ok else "tcp"
 
     def _setup(self) -> None:
         cfg = self.cfg
@@ -148,6 +149,11 @@ class ConvEngine:
                 from .parallel.shm_backend import ShmTile
                 self._impl = ShmTile(self.grid, self.rank, self.filter, cfg.halo_depth, cfg.threads, self.dist,
                                      timeout_ms=cfg.timeout_ms)
+                return
+            if self.cpu_transport == "tcp":
+                from .parallel.net_backend import NetTile
+                self._impl = NetTile(self.grid, self.rank, self.filter, cfg.halo_depth, cfg.threads, self.dist,
+                                     timeout_ms=max(cfg.timeout_ms, 30_000.0))
                 return
             from .parallel.host_backend import HostTile
             # messages are dear (gloo: 0.5-2 ms per exchange of eight): by default trade them for a 6-deep halo and

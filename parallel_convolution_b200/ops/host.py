@@ -91,6 +91,18 @@ def lib() -> C.CDLL:
         fn.restype = None
     L.pconv_shm_run.argtypes = [C.c_void_p, C.c_int, i64, i64, i64, i64, C.POINTER(C.c_int32), fsp, C.c_int,
                                 C.c_int, C.c_int, C.c_double, C.POINTER(i64)]
+    L.pconv_net_init.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_double]
+    L.pconv_net_init.restype = C.c_void_p
+    L.pconv_net_close.argtypes = [C.c_void_p]
+    L.pconv_net_close.restype = None
+    L.pconv_net_error.argtypes = [C.c_void_p]
+    L.pconv_net_error.restype = C.c_char_p
+    L.pconv_net_barrier.argtypes = [C.c_void_p]
+    L.pconv_net_max.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.pconv_net_tile_pitch.argtypes = [i64, C.c_int, C.c_int]
+    L.pconv_net_tile_pitch.restype = i64
+    L.pconv_net_run.argtypes = [C.c_void_p, i64, i64, C.c_int, i64, i64, i64, i64, C.POINTER(C.c_int32), u8p, u8p, fsp,
+                                C.c_int, C.c_int, C.c_int, C.POINTER(i64)]
     return L
 
 
@@ -266,6 +278,55 @@ class ShmSegment:
             self.close()
         except Exception:
             pass
+
+
+class NetComm:
+    """A rank's end of the TCP mesh of csrc/host/net_ranks.cpp (rendezvous through rank 0 at host:port;
+    ``master_fd`` hands rank 0 an already listening socket)."""
+
+    def __init__(self, rank: int, world: int, host: str, port: int, master_fd: int = -1, timeout_s: float = 120.0):
+        self._h = lib().pconv_net_init(rank, world, os.fsencode(host), port, master_fd, timeout_s)
+        if not self._h:
+            raise OSError(f"rank {rank}: cannot join the TCP mesh at {host}:{port}")
+        self.rank, self.world = rank, world
+
+    def _check(self, rc: int, what: str) -> int:
+        if rc < 0:
+            raise OSError(-rc, f"{what}: {lib().pconv_net_error(self._h).decode()}")
+        return rc
+
+    def barrier(self) -> None:
+        self._check(lib().pconv_net_barrier(self._h), "barrier")
+
+    def max(self, v: float) -> float:
+        x = C.c_double(v)
+        self._check(lib().pconv_net_max(self._h, C.byref(x)), "max over ranks")
+        return float(x.value)
+
+    def run(self, shape: tuple[int, int, int], tile: tuple[int, int, int, int], nbr: list[int], bufs: tuple[np.ndarray, np.ndarray],
+            f: FilterSpec, loops: int, k: int, threads: int = 1) -> tuple[int, int]:
+        """``shape`` = (H, W, C) of the image, ``tile`` = (row0, rows, col0, cols); ``bufs``: two zero-framed
+        (rows + 2k, pitch) arrays, input in bufs[0]. Returns (index of the buffer holding the result, exchanges)."""
+        arr = (C.c_int32 * 9)(*[int(v) for v in nbr])
+        nx = C.c_int64(0)
+        rc = lib().pconv_net_run(self._h, shape[0], shape[1], shape[2], tile[0], tile[1], tile[2], tile[3], arr,
+                                 _ptr(bufs[0]), _ptr(bufs[1]), C.byref(f), loops, k, max(1, int(threads)), C.byref(nx))
+        return self._check(rc, "halo exchange"), int(nx.value)
+
+    def close(self) -> None:
+        if self._h:
+            lib().pconv_net_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def net_tile_pitch(cols: int, Cn: int, k: int) -> int:
+    return int(lib().pconv_net_tile_pitch(cols, Cn, k))
 
 
 def cpu_convolve(src: np.ndarray, dst: np.ndarray, halo: int, Cn: int, f: FilterSpec,

@@ -25,7 +25,7 @@ def _torchrun(nproc: int, args: list[str], timeout: int = 240, **extra_env) -> s
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
 
 
-@pytest.mark.parametrize("transport", ["gloo", "shm"])
+@pytest.mark.parametrize("transport", ["gloo", "shm", "tcp"])
 @pytest.mark.parametrize("nproc,extra", [
     (2, []),
     (4, ["--halo-depth", "3", "--filter", "sharpen"]),          # 2x2: exercises the diagonal cells
