@@ -3,8 +3,10 @@
 ranks of one node, one exchange per iteration (k = 1) unless stated. Arms:
 
   shm_k1 / shm_k6   ranks share the image in /dev/shm, one epoch counter per rank (csrc/host/shm_ranks.cpp)
-  gloo_k1           the same ranks trading eight gloo messages per iteration (parallel/host_backend.py):
-                    the reference's schedule (post -> interior -> wait -> border ring, mpi/mpi_conv.c:164-248)
+  tcp_k1 / tcp_k6   private tiles, eight packed strips per exchange over the native TCP mesh
+                    (csrc/host/net_ranks.cpp): the reference's schedule (post -> interior -> wait -> border ring,
+                    mpi/mpi_conv.c:164-248)
+  gloo_k1           the same schedule with gloo messages driven from Python (parallel/host_backend.py)
   reference         unmodified mpi/mpi_conv.c (-O3) under baseline/mpi_shim: 4 messages per iteration
 
 and for each the same tile alone on one rank (no neighbour): the difference is the exposed cost of an exchange.
@@ -61,7 +63,9 @@ def main():
             W, Hh = gc * E, gr * E
             row = {"tile_edge": E, "ranks": world, "grid": f"{gr}x{gc}", "loops": a.loops,
                    "halo_bytes_per_exchange_k1": 4 * E + 4}
-            for key, transport, k in (("shm_k1", "shm", 1), ("shm_k6", "shm", 6), ("gloo_k1", "gloo", 1)):
+            arms = (("shm_k1", "shm", 1), ("shm_k6", "shm", 6), ("tcp_k1", "tcp", 1), ("tcp_k6", "tcp", 6),
+                    ("gloo_k1", "gloo", 1))
+            for key, transport, k in arms:
                 if world == 1:
                     break
                 eng = ConvEngine(width=W, height=Hh, channels=1, filter=f, backend="cpu", grid=(gr, gc), halo_depth=k,
@@ -84,7 +88,7 @@ def main():
                     dt = time.perf_counter() - t0
                     solo = dt if solo is None else min(solo, dt)
                 row["solo_us_per_iter"] = round(solo * 1e6 / a.loops, 2)
-                for key in ("shm_k1", "shm_k6", "gloo_k1"):
+                for key, _, _ in arms:
                     if key + "_us_per_iter" in row:
                         row[key + "_exposed_us_per_iter"] = round(row[key + "_us_per_iter"] - row["solo_us_per_iter"], 2)
                 if have_ref:
