@@ -28,6 +28,12 @@ the reference's own end-to-end number (its only timer wraps all of that, cuda/ma
 W warm-up runs, K timed runs of 100 iterations. A second row reports the same sources compiled with
 ``-arch=sm_100a``. It exists only for N=1 — the reference has no multi-GPU program
 (SURVEY.md §0).
+
+CPU side of the same box, for the record (neither touches the GPU numbers): the reference arm adds
+``config.mpi_conv_same_box`` — the unmodified ``mpi/mpi_conv.c`` (-O3, single-node MPI stand-in
+``baseline/mpi_shim``) at 1/2/4/8 processes in the published tables' setting (RGB, 20 iterations, its own loop
+timer); our arm adds ``config.cpu_engine_same_box`` — the native CPU engine with 1 and 8 threads and
+``pconv_native -np N --cpu`` ranks on the same setting.
 """
 from __future__ import annotations
 
